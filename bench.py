@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: Gbit/s scanned on the snort_16 NFA (BASELINE.json).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mix wmix|whi|wlo|uniform]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: 1 Mi independent 1500-byte packet streams per GPU
+(BASELINE.json configs[2]; configs[3] at N > 1 -- weak scaling, N Mi streams in total, contiguous shards,
+one NCCL all-reduce of the per-state match counts per step).  The batch (1.6 GB per GPU) is far larger
+than the 126 MB L2, so every step streams its input from HBM.
+
+  value        : whole-job Gbit/s with the batch already resident in HBM (CUDA events, max over ranks)
+  e2e          : the same metric through rfb_scan() with HOST buffers (pinned H2D of the batch, kernels,
+                 D2H of counts + match records inside the timed region)
+  roofline     : HBM roofline of the scan kernel -- algorithmic bytes = 1 byte per symbol scanned
+  cpu_baseline : the cycle-level CPU restatement of the reference design (oracle/oracle_a.c, the stand-in
+                 for the "Verilated reference": no HDL simulator exists in this image) on a bounded sample
+  --impl reference : that same CPU restatement as the timed arm, all host threads
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+STREAM_LEN = 1500
+STRIDE = 1536
+SEED = 0x5EED0001
+METRIC = "gbit_per_s_scanned_snort16"
+
+
+def load_ruleset(name="snort_16"):
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    return z["entries"], int(z["n_states"]), z["lo"], z["hi"]
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms (oracle = test/baseline infrastructure; never on the product path)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(E, n_states, lo, hi, mix, n_pairs, first_stream=0):
+    from regex_fpga_b200 import workloads as WL
+    return WL.make_batch_numpy(mix, lo, hi, 2 * n_pairs, STREAM_LEN, STRIDE, SEED, first_stream)
+
+
+def run_cpu_reference(E, n_states, sample, n_pairs, threads):
+    """Cycle-level oracle (FPGA.v + ROM + testbench), one (lo,hi) stream pair per thread at a time.
+    TB semantics: an M-entry trace pair yields 2*(M-1) symbol steps."""
+    from oracle import oracle_py as O
+    t0 = time.perf_counter()
+    r = O.a_run_many(E, n_states, sample, n_pairs, STRIDE, STREAM_LEN, n_threads=threads, fast_idle=False)
+    dt = time.perf_counter() - t0
+    return r["symbols"], r["cycles"], dt
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import oracle_py as O
+    O.build()
+    E, n_states, lo, hi = load_ruleset()
+    threads = os.cpu_count() or 1
+    n_pairs = max(threads, 8)
+    times, syms, cycles = [], 0, 0
+    for it in range(args.warmup + args.steps):
+        sample = cpu_sample(E, n_states, lo, hi, args.mix, n_pairs, first_stream=2 * n_pairs * it)
+        s, c, dt = run_cpu_reference(E, n_states, sample, n_pairs, threads)
+        if it >= args.warmup:
+            times.append(dt); syms += s; cycles += c
+    total = sum(times)
+    gbit = syms * 8 / total / 1e9
+    desc = f"{n_pairs} (lo,hi) stream pairs x {STREAM_LEN} entries per step ({2 * n_pairs * (STREAM_LEN - 1)} symbols)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbit, "unit": "Gbit/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / max(1, args.steps) * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": gbit, "unit": "Gbit/s", "cores": threads, "kind": "port", "sample": desc,
+                         "simulated_cycles_per_s": cycles / total,
+                         "note": "cycle-level C restatement of Design/FPGA.v + testbench (oracle/oracle_a.c); "
+                                 "the Verilog cannot be simulated here (no Verilator/Icarus in the image)"},
+        "e2e": {"value": gbit, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"snort_16 NFA (9514 states, 79856 transitions) over {args.streams} synthetic "
+                        f"{STREAM_LEN}-byte packet streams per GPU ({args.mix}: windows of the shipped lo/hi "
+                        f"traces at splitmix64 offsets, seed {SEED:#x})",
+            "streams_per_gpu": args.streams, "streams_total": args.streams * world, "stream_bytes": STREAM_LEN,
+            "stride": STRIDE, "n_steps_per_stream": STREAM_LEN, "mix": args.mix,
+            "sharding": f"{world} x contiguous stream shards, NCCL all-reduce of per-state counts" if world > 1
+                        else "single GPU",
+            "l2": "input batch (1.6 GB/GPU) >> 126 MB L2, no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def ours_arm(args, rank, world, local_rank):
+    import torch
+    import regex_fpga_b200 as R
+    from regex_fpga_b200 import workloads as WL
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the scan has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    E, n_states, lo, hi = load_ruleset()
+    ctx = R.Context(local_rank)
+    nfa = ctx.nfa_from_entries(E)
+    n = args.streams
+    first = rank * n
+    batch = WL.make_batch_torch(args.mix, lo, hi, n, dev, STREAM_LEN, STRIDE, SEED, first)
+    counts = torch.zeros(n_states, dtype=torch.int64, device=dev)
+    cap = args.record_capacity
+    recs = torch.empty(cap * 3, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    sym_per_step = n * STREAM_LEN
+
+    def step():
+        r = nfa.scan_device(batch.data_ptr(), batch.numel(), n, STREAM_LEN, STRIDE, counts.data_ptr(),
+                            recs.data_ptr(), cap, flags=R.SCAN_ASYNC, cuda_stream=stream.cuda_stream,
+                            stream_id_base=first)
+        if dist is not None:
+            dist.all_reduce(counts)          # final exchange of the path: per-state match counts
+        return r
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        r = step()
+    barrier()
+    res0 = nfa.collect(r) if args.warmup else None
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        r = step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    res = nfa.collect(r)
+    kernel_ms.append(res.gpu_ms)
+    ms_total = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * sym_per_step * 8 / (ms_per_step * 1e-3) / 1e9
+
+    # ---- per-kernel time for the roofline: the library brackets its kernels with CUDA events ----
+    # (one more un-overlapped step so that gpu_ms is exactly lane kernel + rescan kernel of one pass)
+    r = nfa.scan_device(batch.data_ptr(), batch.numel(), n, STREAM_LEN, STRIDE, counts.data_ptr(), recs.data_ptr(), cap,
+                        cuda_stream=stream.cuda_stream, stream_id_base=first)
+    scan_ms = float(r.gpu_ms)
+    n_matches, n_rescanned, n_dropped = int(r.n_matches), int(r.n_rescanned), int(r.n_dropped)
+    peak, peak_src = measured_peaks()
+    achieved = sym_per_step * 1.0 / (scan_ms * 1e-3) / 1e9     # GB/s, 1 algorithmic byte per symbol
+
+    # ---- e2e through the host-pointer API (pinned host batch -> H2D -> kernels -> D2H results) ----
+    host = torch.empty((n, STRIDE), dtype=torch.uint8, pin_memory=True)
+    host.copy_(batch)
+    torch.cuda.synchronize()
+    host_np = host.numpy()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    out = nfa.scan(host_np, n, n_steps=STREAM_LEN, stride=STRIDE, record_capacity=cap, flags=0,
+                   stream_id_base=first)   # warm-up (allocates the staging buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = nfa.scan(host_np, n, n_steps=STREAM_LEN, stride=STRIDE, record_capacity=cap, flags=0,
+                       stream_id_base=first)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_val = world * sym_per_step * 8 / e2e_s / 1e9
+    assert out.n_matches == n_matches, "host-pointer and device-pointer scans disagree"
+    h2d = int(host_np.size)
+    d2h = int(n_states * 8 + out.n_records * 12 + 32)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "Gbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "s_per_step": e2e_s},
+            "gpu_launches": 2 * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "scan_lane_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac_of_8000": achieved / 8000.0, "scan_ms": scan_ms,
+                         "algorithmic_bytes_per_launch": sym_per_step},
+            "matches_per_step_rank0": n_matches, "rescanned_streams": n_rescanned, "records_dropped": n_dropped,
+            "symbols_per_s": world * sym_per_step / (ms_per_step * 1e-3),
+            "image": nfa.info,
+        }
+        if world == 1 and not args.no_cpu:
+            from oracle import oracle_py as O
+            O.build()
+            threads = os.cpu_count() or 1
+            n_pairs = max(threads, 8) * args.cpu_pairs_per_core
+            sample = cpu_sample(E, n_states, lo, hi, args.mix, n_pairs)
+            s, c, dt = run_cpu_reference(E, n_states, sample, n_pairs, threads)
+            t0 = time.perf_counter()
+            fb = O.b_scan_many(E, n_states, sample, 2 * n_pairs, STRIDE, STREAM_LEN, n_threads=threads, want_recs=False)
+            dtb = time.perf_counter() - t0
+            line["cpu_baseline"] = {
+                "value": s * 8 / dt / 1e9, "unit": "Gbit/s", "cores": threads, "kind": "port",
+                "sample": f"{n_pairs} (lo,hi) stream pairs x {STREAM_LEN} entries of the same {args.mix} workload "
+                          f"({s} symbols, {dt:.1f} s wall)",
+                "simulated_cycles_per_s": c / dt,
+                "note": "oracle A = cycle-level C restatement of Design/FPGA.v + testbench; the Verilog itself cannot "
+                        "be simulated in this image",
+                "functional_port_gbit_s": 2 * n_pairs * STREAM_LEN * 8 / dtb / 1e9,
+            }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mix", default="wmix", choices=["wmix", "whi", "wlo", "uniform"])
+    ap.add_argument("--streams", type=int, default=1 << 20, help="streams per GPU")
+    ap.add_argument("--record-capacity", type=int, default=1 << 22)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-pairs-per-core", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        ours_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

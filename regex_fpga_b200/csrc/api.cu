@@ -1,0 +1,419 @@
+// api.cu -- the C ABI (include/regex_fpga_b200.h) over the host model and the kernels.
+#include "device.h"
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace rfb;
+
+static thread_local std::string g_err = "";
+
+struct rfb_ctx {
+    int device = 0;
+    int n_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    ScanGlobals *g = nullptr;          // device
+    ScanGlobals *g_host = nullptr;     // pinned
+    uint2 *rescan = nullptr;
+    size_t rescan_cap = 0;
+    // grow-only staging for rfb_scan (host-pointer variant)
+    uint8_t *d_data = nullptr; size_t d_data_cap = 0;
+    unsigned long long *d_offsets = nullptr; size_t d_offsets_cap = 0;
+    unsigned int *d_steps = nullptr; size_t d_steps_cap = 0;
+    unsigned long long *d_counts = nullptr; size_t d_counts_cap = 0;
+    rfb_match *d_records = nullptr; size_t d_records_cap = 0;
+    // state of the last enqueued scan (for rfb_scan_collect)
+    cudaStream_t last_stream = nullptr;
+    unsigned long long last_symbols = 0;
+    bool last_ragged = false;
+    uint32_t last_launches = 0;
+    std::string err;
+};
+
+struct rfb_nfa {
+    rfb_ctx *ctx = nullptr;
+    Nfa host;
+    Image img;
+    NfaDev dev{};
+    uint32_t *d_entries = nullptr;
+    uint8_t *d_blob = nullptr;
+    uint32_t *d_orig = nullptr;
+};
+
+static int fail(rfb_ctx *ctx, int code, const std::string &msg) {
+    g_err = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+static int cuda_fail(rfb_ctx *ctx, cudaError_t e, const char *what) {
+    return fail(ctx, RFB_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(ctx, call)                                             \
+    do {                                                          \
+        cudaError_t e_ = (call);                                  \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);  \
+    } while (0)
+
+template <class T>
+static cudaError_t ensure(T *&p, size_t &cap, size_t want) {
+    if (want <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    size_t n = std::max<size_t>(want, 16);
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&p), n * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+}
+
+static void fill_info(const Nfa &host, const Image &img, rfb_nfa_info *info) {
+    std::memset(info, 0, sizeof *info);
+    info->n_states = host.n_states;
+    info->n_transitions = host.nnz;
+    info->n_accepting = host.n_accepting;
+    info->n_entries = (uint32_t)host.entries.size();
+    info->image_ok = img.ok ? 1u : 0u;
+    info->image_bytes = img.h.blob_bytes;
+    info->n_sticky = img.n_sticky;
+    info->sticky_words = img.h.sticky_words;
+    info->n_slots = img.h.n_slots;
+    info->n_class_sets = img.h.n_sets;
+    info->bucket_bits = img.h.bucket_bits;
+}
+
+static ImageOptions default_image_options() {
+    ImageOptions opt;
+    if (const char *s = std::getenv("RFB_STICKY_WORDS")) opt.sticky_words = std::atoi(s);
+    if (const char *s = std::getenv("RFB_BUCKET_BITS")) opt.bucket_bits = std::atoi(s);
+    if (const char *s = std::getenv("RFB_STICKY_MIN_SELF")) opt.sticky_min_self = std::atoi(s);
+    opt.max_bytes = (uint32_t)(MAX_DYN_SMEM - (size_t)LANE_CAP * LANE_THREADS * sizeof(uint16_t) - 64);
+    return opt;
+}
+
+extern "C" {
+
+int rfb_abi_version(void) { return RFB_ABI_VERSION; }
+
+const char *rfb_last_error(const rfb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int rfb_ctx_create(int device_id, rfb_ctx **out) {
+    if (!out) return fail(nullptr, RFB_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return fail(nullptr, RFB_E_NODEVICE, std::string("no usable CUDA device (this library has no CPU path): ") +
+                                                 (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device_id < 0 || device_id >= n) return fail(nullptr, RFB_E_INVALID, "device_id out of range");
+    rfb_ctx *ctx = new (std::nothrow) rfb_ctx();
+    if (!ctx) return fail(nullptr, RFB_E_NOMEM, "out of host memory");
+    ctx->device = device_id;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device_id)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device_id)) != cudaSuccess) {
+        delete ctx;
+        return cuda_fail(nullptr, e, "cudaSetDevice");
+    }
+    if (prop.major < 10) {
+        delete ctx;
+        return fail(nullptr, RFB_E_NODEVICE, std::string("device ") + prop.name + " is sm_" + std::to_string(prop.major) +
+                                                 std::to_string(prop.minor) + "; this library is built for sm_100a only");
+    }
+    ctx->n_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&ctx->g), sizeof(ScanGlobals))) != cudaSuccess ||
+        (e = cudaMallocHost(reinterpret_cast<void **>(&ctx->g_host), sizeof(ScanGlobals))) != cudaSuccess ||
+        (e = configure_kernels()) != cudaSuccess) {
+        int rc = cuda_fail(nullptr, e, "context setup");
+        rfb_ctx_destroy(ctx);
+        return rc;
+    }
+    *out = ctx;
+    return RFB_OK;
+}
+
+void rfb_ctx_destroy(rfb_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    cudaFree(ctx->g);
+    if (ctx->g_host) cudaFreeHost(ctx->g_host);
+    cudaFree(ctx->rescan);
+    cudaFree(ctx->d_data); cudaFree(ctx->d_offsets); cudaFree(ctx->d_steps);
+    cudaFree(ctx->d_counts); cudaFree(ctx->d_records);
+    delete ctx;
+}
+
+// ---- transition memory ---------------------------------------------------------------------------
+int rfb_nfa_from_entries(rfb_ctx *ctx, const uint32_t *entries, size_t n_entries, int64_t n_states, rfb_nfa **out) {
+    if (!ctx || !out || !entries) return fail(ctx, RFB_E_INVALID, "NULL argument");
+    *out = nullptr;
+    rfb_nfa *nfa = new (std::nothrow) rfb_nfa();
+    if (!nfa) return fail(ctx, RFB_E_NOMEM, "out of host memory");
+    nfa->ctx = ctx;
+    std::string err;
+    int rc = nfa_from_entries(entries, n_entries, n_states, nfa->host, err);
+    if (rc) { delete nfa; return fail(ctx, rc, err); }
+    ImageOptions opt = default_image_options();
+    rc = image_build(nfa->host, opt, nfa->img, err);
+    if (rc) { delete nfa; return fail(ctx, rc, err); }
+
+    cudaSetDevice(ctx->device);
+    const Nfa &h = nfa->host;
+    cudaError_t e;
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_entries), h.entries.size() * 4)) != cudaSuccess ||
+        (e = cudaMemcpy(nfa->d_entries, h.entries.data(), h.entries.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+        rfb_nfa_destroy(nfa);
+        return cuda_fail(ctx, e, "upload CSR");
+    }
+    nfa->dev.n_states = h.n_states;
+    nfa->dev.row_ptr = nfa->d_entries;
+    nfa->dev.trans = nfa->d_entries + h.n_states + 1;
+    if (nfa->img.ok) {
+        const Image &im = nfa->img;
+        if ((e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_blob), im.blob.size())) != cudaSuccess ||
+            (e = cudaMemcpy(nfa->d_blob, im.blob.data(), im.blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_orig), im.orig_of_id.size() * 4)) != cudaSuccess ||
+            (e = cudaMemcpy(nfa->d_orig, im.orig_of_id.data(), im.orig_of_id.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            rfb_nfa_destroy(nfa);
+            return cuda_fail(ctx, e, "upload execution image");
+        }
+        nfa->dev.blob = nfa->d_blob;
+        nfa->dev.orig_of_id = nfa->d_orig;
+        nfa->dev.h = im.h;
+    }
+    *out = nfa;
+    return RFB_OK;
+}
+
+int rfb_nfa_load_coe(rfb_ctx *ctx, const char *path, int64_t n_states, rfb_nfa **out) {
+    if (!ctx || !path || !out) return fail(ctx, RFB_E_INVALID, "NULL argument");
+    std::vector<uint32_t> e;
+    std::string err;
+    int rc = coe_parse_file(path, e, err);
+    if (rc) return fail(ctx, rc, err);
+    return rfb_nfa_from_entries(ctx, e.data(), e.size(), n_states, out);
+}
+
+void rfb_nfa_destroy(rfb_nfa *nfa) {
+    if (!nfa) return;
+    if (nfa->ctx) cudaSetDevice(nfa->ctx->device);
+    cudaFree(nfa->d_entries); cudaFree(nfa->d_blob); cudaFree(nfa->d_orig);
+    delete nfa;
+}
+
+int rfb_nfa_get_info(const rfb_nfa *nfa, rfb_nfa_info *info) {
+    if (!nfa || !info) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    fill_info(nfa->host, nfa->img, info);
+    return RFB_OK;
+}
+
+int rfb_image_check(const uint32_t *entries, size_t n_entries, int64_t n_states, int sticky_words, int bucket_bits,
+                    rfb_nfa_info *info) {
+    if (!entries || !info) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    Nfa host;
+    Image img;
+    std::string err;
+    int rc = nfa_from_entries(entries, n_entries, n_states, host, err);
+    if (rc) return fail(nullptr, rc, err);
+    ImageOptions opt = default_image_options();
+    if (sticky_words > 0) opt.sticky_words = sticky_words;
+    if (bucket_bits > 0) opt.bucket_bits = bucket_bits;
+    rc = image_build(host, opt, img, err);
+    if (rc) return fail(nullptr, rc, err);
+    fill_info(host, img, info);
+    if (!img.ok) g_err = img.why_not;
+    return RFB_OK;
+}
+
+int rfb_nfa_get_entries(const rfb_nfa *nfa, uint32_t *entries, size_t capacity) {
+    if (!nfa || !entries) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    if (capacity < nfa->host.entries.size()) return fail(nfa->ctx, RFB_E_INVALID, "capacity too small");
+    std::memcpy(entries, nfa->host.entries.data(), nfa->host.entries.size() * 4);
+    return RFB_OK;
+}
+
+// ---- host-side format helpers ---------------------------------------------------------------------
+int rfb_trace_load_mem(const char *path, uint8_t **bytes, size_t *n) {
+    if (!path || !bytes || !n) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    std::vector<uint8_t> v;
+    std::string err;
+    int rc = mem_parse_file(path, v, err);
+    if (rc) return fail(nullptr, rc, err);
+    *bytes = static_cast<uint8_t *>(std::malloc(v.size() ? v.size() : 1));
+    if (!*bytes) return fail(nullptr, RFB_E_NOMEM, "out of host memory");
+    std::memcpy(*bytes, v.data(), v.size());
+    *n = v.size();
+    return RFB_OK;
+}
+int rfb_trace_write_mem(const char *path, const uint8_t *bytes, size_t n) {
+    if (!path || (!bytes && n)) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    std::string err;
+    int rc = mem_write_file(path, bytes, n, err);
+    return rc ? fail(nullptr, rc, err) : RFB_OK;
+}
+int rfb_coe_parse(const char *path, uint32_t **entries, size_t *n_entries) {
+    if (!path || !entries || !n_entries) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    std::vector<uint32_t> v;
+    std::string err;
+    int rc = coe_parse_file(path, v, err);
+    if (rc) return fail(nullptr, rc, err);
+    *entries = static_cast<uint32_t *>(std::malloc(v.size() * 4));
+    if (!*entries) return fail(nullptr, RFB_E_NOMEM, "out of host memory");
+    std::memcpy(*entries, v.data(), v.size() * 4);
+    *n_entries = v.size();
+    return RFB_OK;
+}
+int rfb_coe_write(const char *path, const uint32_t *entries, size_t n_entries, int style) {
+    if (!path || !entries) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    std::string err;
+    int rc = coe_write_file(path, entries, n_entries, style, err);
+    return rc ? fail(nullptr, rc, err) : RFB_OK;
+}
+int64_t rfb_coe_detect_size(const uint32_t *entries, size_t n_entries) {
+    if (!entries) return -1;
+    return detect_size(entries, n_entries);
+}
+void rfb_free(void *p) { std::free(p); }
+uint32_t rfb_tb_steps(uint32_t trace_entries) { return trace_entries ? trace_entries - 1 : 0; }
+
+// ---- the scan ----------------------------------------------------------------------------------------
+static int check_batch(rfb_ctx *ctx, const rfb_batch *b, bool host) {
+    if (!b) return fail(ctx, RFB_E_INVALID, "batch is NULL");
+    if (b->n_streams > 0xFFFFFFFFull) return fail(ctx, RFB_E_INVALID, "n_streams exceeds 2^32-1 (stream ids are 32-bit)");
+    if (b->n_streams && !b->data && b->data_bytes) return fail(ctx, RFB_E_INVALID, "data is NULL");
+    if (host) {  // host pointers can be bounds-checked
+        for (uint64_t s = 0; s < b->n_streams; s++) {
+            const uint64_t off = b->offsets ? b->offsets[s] : s * b->stride;
+            const uint64_t len = b->steps ? b->steps[s] : b->n_steps;
+            if (off + len > b->data_bytes) return fail(ctx, RFB_E_INVALID, "stream " + std::to_string(s) + " extends past data_bytes");
+        }
+    } else if (!b->offsets && !b->steps && b->n_streams) {
+        if ((b->n_streams - 1) * b->stride + b->n_steps > b->data_bytes) return fail(ctx, RFB_E_INVALID, "streams extend past data_bytes");
+    }
+    return RFB_OK;
+}
+
+int rfb_scan_collect(rfb_ctx *ctx, rfb_result *res) {
+    if (!ctx || !res) return fail(ctx, RFB_E_INVALID, "NULL argument");
+    cudaSetDevice(ctx->device);
+    CU(ctx, cudaMemcpyAsync(ctx->g_host, ctx->g, sizeof(ScanGlobals), cudaMemcpyDeviceToHost, ctx->last_stream));
+    CU(ctx, cudaStreamSynchronize(ctx->last_stream));
+    const ScanGlobals &g = *ctx->g_host;
+    res->n_matches = g.n_matches;
+    res->n_records = res->records ? std::min<uint64_t>(g.n_matches, res->record_capacity) : 0;
+    res->n_dropped = g.n_matches - res->n_records;
+    res->n_symbols = ctx->last_ragged ? g.n_symbols : ctx->last_symbols;
+    res->n_rescanned = g.n_rescan;
+    res->n_launches = ctx->last_launches;
+    float ms = 0.f;
+    CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    res->gpu_ms = ms;
+    return RFB_OK;
+}
+
+int rfb_scan_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flags, void *cuda_stream, rfb_result *res) {
+    if (!ctx || !nfa || !res) return fail(ctx, RFB_E_INVALID, "NULL argument");
+    if (nfa->ctx != ctx) return fail(ctx, RFB_E_INVALID, "nfa belongs to another context");
+    int rc = check_batch(ctx, b, false);
+    if (rc) return rc;
+    if (flags & RFB_SCAN_SORT_RECORDS) return fail(ctx, RFB_E_UNSUPPORTED, "RFB_SCAN_SORT_RECORDS is only available through rfb_scan");
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
+    if (ctx->rescan_cap < b->n_streams) CU(ctx, ensure(ctx->rescan, ctx->rescan_cap, (size_t)b->n_streams));
+
+    if (flags & RFB_SCAN_ACCUMULATE) {
+        CU(ctx, cudaMemsetAsync(&ctx->g->next_stream, 0, 4 * sizeof(unsigned int), st));
+    } else {
+        CU(ctx, cudaMemsetAsync(ctx->g, 0, sizeof(ScanGlobals), st));
+        if (res->counts && !(flags & RFB_SCAN_NO_COUNTS))
+            CU(ctx, cudaMemsetAsync(res->counts, 0, (size_t)nfa->host.n_states * sizeof(uint64_t), st));
+    }
+    BatchDev bd;
+    bd.data = b->data; bd.n_streams = b->n_streams; bd.stride = b->stride;
+    bd.offsets = reinterpret_cast<const unsigned long long *>(b->offsets);
+    bd.steps = b->steps; bd.n_steps = b->n_steps; bd.stream_id_base = b->stream_id_base;
+    OutDev od;
+    od.counts = (flags & RFB_SCAN_NO_COUNTS) ? nullptr : reinterpret_cast<unsigned long long *>(res->counts);
+    od.records = res->records; od.capacity = res->records ? res->record_capacity : 0;
+    od.g = ctx->g; od.rescan = ctx->rescan;
+
+    uint32_t launches = 0;
+    CU(ctx, cudaEventRecord(ctx->ev0, st));
+    if (b->n_streams) {
+        const bool lane = nfa->img.ok && !(flags & RFB_SCAN_FORCE_WARP);
+        if (lane) {
+            CU(ctx, launch_scan_lane(nfa->dev, bd, od, ctx->n_sms, st)); launches++;
+            CU(ctx, launch_scan_warp(nfa->dev, bd, od, true, ctx->n_sms, st)); launches++;
+        } else {
+            CU(ctx, launch_scan_warp(nfa->dev, bd, od, false, ctx->n_sms, st)); launches++;
+        }
+    }
+    CU(ctx, cudaEventRecord(ctx->ev1, st));
+    ctx->last_stream = st;
+    ctx->last_ragged = b->steps != nullptr;
+    ctx->last_symbols = b->steps ? 0 : b->n_streams * (unsigned long long)b->n_steps;
+    ctx->last_launches = launches;
+    if (flags & RFB_SCAN_ASYNC) return RFB_OK;
+    return rfb_scan_collect(ctx, res);
+}
+
+int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flags, rfb_result *res) {
+    if (!ctx || !nfa || !res) return fail(ctx, RFB_E_INVALID, "NULL argument");
+    int rc = check_batch(ctx, b, true);
+    if (rc) return rc;
+    cudaSetDevice(ctx->device);
+    cudaStream_t st = ctx->stream;
+    const size_t padded = ((size_t)b->data_bytes + 15) / 16 * 16 + 16;
+    CU(ctx, ensure(ctx->d_data, ctx->d_data_cap, padded));
+    if (b->data_bytes) CU(ctx, cudaMemcpyAsync(ctx->d_data, b->data, b->data_bytes, cudaMemcpyHostToDevice, st));
+    rfb_batch db = *b;
+    db.data = ctx->d_data;
+    if (b->offsets) {
+        CU(ctx, ensure(ctx->d_offsets, ctx->d_offsets_cap, (size_t)b->n_streams));
+        CU(ctx, cudaMemcpyAsync(ctx->d_offsets, b->offsets, b->n_streams * 8, cudaMemcpyHostToDevice, st));
+        db.offsets = reinterpret_cast<const uint64_t *>(ctx->d_offsets);
+    }
+    if (b->steps) {
+        CU(ctx, ensure(ctx->d_steps, ctx->d_steps_cap, (size_t)b->n_streams));
+        CU(ctx, cudaMemcpyAsync(ctx->d_steps, b->steps, b->n_streams * 4, cudaMemcpyHostToDevice, st));
+        db.steps = ctx->d_steps;
+    }
+    rfb_result dr = *res;
+    const bool want_counts = res->counts && !(flags & RFB_SCAN_NO_COUNTS);
+    if (want_counts) {
+        CU(ctx, ensure(ctx->d_counts, ctx->d_counts_cap, (size_t)nfa->host.n_states));
+        dr.counts = reinterpret_cast<uint64_t *>(ctx->d_counts);
+    } else dr.counts = nullptr;
+    if (res->records && res->record_capacity) {
+        CU(ctx, ensure(ctx->d_records, ctx->d_records_cap, (size_t)res->record_capacity));
+        dr.records = ctx->d_records;
+    } else { dr.records = nullptr; dr.record_capacity = 0; }
+    rc = rfb_scan_device(ctx, nfa, &db, flags & ~(RFB_SCAN_SORT_RECORDS | RFB_SCAN_ASYNC | RFB_SCAN_ACCUMULATE), st, &dr);
+    if (rc) return rc;
+    if (want_counts) CU(ctx, cudaMemcpyAsync(res->counts, ctx->d_counts, (size_t)nfa->host.n_states * 8, cudaMemcpyDeviceToHost, st));
+    if (dr.n_records) CU(ctx, cudaMemcpyAsync(res->records, ctx->d_records, dr.n_records * sizeof(rfb_match), cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    res->n_matches = dr.n_matches; res->n_records = dr.n_records; res->n_dropped = dr.n_dropped;
+    res->n_symbols = dr.n_symbols; res->n_rescanned = dr.n_rescanned; res->gpu_ms = dr.gpu_ms;
+    res->n_launches = dr.n_launches;
+    if ((flags & RFB_SCAN_SORT_RECORDS) && res->n_records > 1) {
+        std::sort(res->records, res->records + res->n_records, [](const rfb_match &x, const rfb_match &y) {
+            if (x.stream != y.stream) return x.stream < y.stream;
+            if (x.pos != y.pos) return x.pos < y.pos;
+            return x.state < y.state;
+        });
+    }
+    return RFB_OK;
+}
+
+int rfb_fpga_cycles(rfb_ctx *ctx, const rfb_nfa *, const uint8_t *, const uint8_t *, uint32_t, uint64_t *) {
+    return fail(ctx, RFB_E_UNSUPPORTED, "rfb_fpga_cycles is not implemented yet");
+}
+
+}  // extern "C"

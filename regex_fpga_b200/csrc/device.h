@@ -1,0 +1,68 @@
+// device.h -- structures shared between the C ABI (api.cu) and the kernels (scan_*.cu).
+#pragma once
+#include "../../include/regex_fpga_b200.h"
+#include "host.h"
+#include <cuda_runtime.h>
+
+namespace rfb {
+
+// Zeroed before every scan; read back (32 bytes) after it.
+struct ScanGlobals {
+    unsigned long long n_matches;   // every accept pulse, recorded or not
+    unsigned long long n_symbols;   // symbol steps executed (ragged batches only; else host-computed)
+    unsigned int next_stream;       // lane kernel: dynamic stream fetch
+    unsigned int n_rescan;          // streams queued for the warp kernel
+    unsigned int next_item;         // warp kernel: dynamic work fetch
+    unsigned int pad;
+};
+
+struct BatchDev {
+    const uint8_t *data;
+    unsigned long long n_streams;
+    unsigned long long stride;
+    const unsigned long long *offsets;  // nullable
+    const unsigned int *steps;          // nullable
+    unsigned int n_steps;
+    unsigned int stream_id_base;
+};
+
+struct OutDev {
+    unsigned long long *counts;  // nullable
+    rfb_match *records;          // nullable
+    unsigned long long capacity;
+    ScanGlobals *g;
+    uint2 *rescan;               // (stream, first pos to report) pairs, capacity n_streams
+};
+
+struct NfaDev {
+    uint32_t n_states;
+    const uint32_t *row_ptr;     // [n_states + 1]
+    const uint32_t *trans;       // [nnz]  {symbol[31:24], target[23:0]}  Design/FPGA.v:888-898
+    // execution image
+    const uint8_t *blob;         // ImageHeader::blob_bytes bytes, 16-byte aligned
+    const uint32_t *orig_of_id;  // [n_slots]
+    ImageHeader h;
+};
+
+// lane kernel geometry
+constexpr int LANE_THREADS = 1024;   // one CTA per SM
+constexpr int LANE_CAP = 16;         // transient-list ring entries per stream (power of two)
+// warp kernel geometry
+constexpr int WARP_THREADS = 256;
+constexpr int WARP_LCAP = 512;       // sparse list entries per warp before it switches to bitmap scans
+
+size_t lane_smem_bytes(const ImageHeader &h);
+size_t warp_smem_bytes(uint32_t n_states, int warps_per_cta);
+
+// Enqueue the lane kernel (one thread per stream, tables in shared memory).
+cudaError_t launch_scan_lane(const NfaDev &nfa, const BatchDev &batch, const OutDev &out, int n_sms,
+                             cudaStream_t stream);
+// Enqueue the general kernel (one warp per stream, CSR in global memory / L2).
+//   from_rescan = false: all streams of the batch;  true: the (stream, first_pos) pairs queued by the
+//   lane kernel -- the count is read on the device, so no host round trip is needed in between.
+cudaError_t launch_scan_warp(const NfaDev &nfa, const BatchDev &batch, const OutDev &out, bool from_rescan,
+                             int n_sms, cudaStream_t stream);
+cudaError_t configure_kernels();
+constexpr size_t MAX_DYN_SMEM = 227 * 1024;   // per-CTA opt-in limit on sm_100
+
+}  // namespace rfb

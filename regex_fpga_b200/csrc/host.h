@@ -1,0 +1,91 @@
+// host.h -- host-side model of the reference's data: file formats, CSR NFA, execution image.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace rfb {
+
+// ---- formats.cpp ------------------------------------------------------------------------------
+// Xilinx .coe BRAM image <-> 32-bit entries (Block_Mem/CSR_BlockMem*.coe; entry 4*line+slot,
+// slot 0 = rd_bus[127:96], Design/FPGA.v:881-884).  Throw-free: return 0 or a negative rfb_status
+// and fill `err`.
+int coe_parse_file(const std::string &path, std::vector<uint32_t> &entries, std::string &err);
+int coe_write_file(const std::string &path, const uint32_t *entries, size_t n, int style,
+                   std::string &err);
+// $readmemh byte traces (Simulation/input_trace_*.mem, testbench_BLK_Mem.sv:34-35).
+int mem_parse_file(const std::string &path, std::vector<uint8_t> &bytes, std::string &err);
+int mem_write_file(const std::string &path, const uint8_t *bytes, size_t n, std::string &err);
+// The image does not store `size` (Design/FPGA.v:26 takes it as a port); -1 if not unique.
+int64_t detect_size(const uint32_t *entries, size_t n);
+
+// ---- nfa.cpp ----------------------------------------------------------------------------------
+struct Nfa {
+    uint32_t n_states = 0;
+    uint32_t nnz = 0;
+    uint32_t n_accepting = 0;
+    std::vector<uint32_t> entries;  // the BRAM image as loaded (row_ptr | transitions | padding)
+    const uint32_t *row_ptr() const { return entries.data(); }
+    const uint32_t *trans() const { return entries.data() + n_states + 1; }  // Design/FPGA.v:773,793
+    uint32_t degree(uint32_t s) const { return row_ptr()[s + 1] - row_ptr()[s]; }
+};
+// Validates and adopts an image.  n_states < 0: auto-detect.
+int nfa_from_entries(const uint32_t *entries, size_t n, int64_t n_states, Nfa &out, std::string &err);
+
+// ---- image.cpp --------------------------------------------------------------------------------
+// Execution image: the CSR re-indexed at load time for the lane kernel (one thread per stream).
+// See DESIGN.md "Execution image" for the layout; image_successors() is its executable definition
+// and image_verify() proves it equivalent to the CSR for every (state, symbol).
+struct ImageOptions {
+    int sticky_words = 0;       // 0 = auto (1 or 2)
+    int sticky_min_self = 16;   // a state is mask-resident if it self-loops on >= this many symbols
+    int bucket_bits = -1;       // -1 = auto; buckets per branching state = 1 << bucket_bits
+    uint32_t max_bytes = 200 * 1024;
+};
+
+struct ImageHeader {  // mirrored on the device (kernels.cuh)
+    uint32_t n_slots;       // entries in tab
+    uint32_t gbase;         // first slot of the branching-state rows
+    uint32_t nsb;           // sticky bits = 64 * sticky_words; ids < nsb are mask-resident
+    uint32_t sticky_words;
+    uint32_t bucket_bits;
+    uint32_t hash_mul;      // bucket(c) = ((c * hash_mul) >> hash_shift) & (nb - 1)
+    uint32_t hash_shift;
+    uint32_t start_id;      // internal id of state 0
+    uint32_t n_sets;
+    // byte offsets of the sections inside the blob (all 16-byte aligned)
+    uint32_t off_tab, off_inj, off_mask, off_memb, off_tlist;
+    uint32_t blob_bytes;
+};
+
+struct Image {
+    bool ok = false;
+    std::string why_not;               // reason when !ok
+    ImageHeader h{};
+    std::vector<uint8_t> blob;         // tab | inj | mask | memb | tlist, staged verbatim into smem
+    std::vector<uint32_t> orig_of_id;  // internal id -> original state id (0xFFFFFFFF: not a state)
+    std::vector<uint32_t> id_of_orig;  // original state id -> internal id
+    uint32_t n_sticky = 0;
+};
+
+// tab entry encoding
+constexpr uint32_t TAB_MORE = 0x80000000u;
+inline uint32_t tab_pack(uint32_t a, uint32_t b, uint32_t tgt, bool more) {
+    return (a & 0xFF) | ((b & 0xFF) << 8) | ((tgt & 0x7FFF) << 16) | (more ? TAB_MORE : 0u);
+}
+// a > b encodes a special: code = (0xFF - a) * 256 + b
+constexpr uint32_t CODE_EMPTY = 0, CODE_ACCEPT = 1, CODE_INDIRECT = 2, CODE_CLASS0 = 256;
+inline uint32_t tab_special(uint32_t code, uint32_t tgt, bool more) {
+    return tab_pack(0xFF - (code >> 8), code & 0xFF, tgt, more);
+}
+
+int image_build(const Nfa &nfa, const ImageOptions &opt, Image &img, std::string &err);
+// Successors of original state s on symbol c as computed THROUGH the image (sorted, original ids);
+// *accepting reports whether the image treats s as accepting.
+void image_successors(const Image &img, uint32_t s, uint32_t c, std::vector<uint32_t> &out,
+                      bool *accepting);
+// Exhaustive equivalence check image == CSR.  Returns 0 or RFB_E_INTERNAL with a message.
+int image_verify(const Nfa &nfa, const Image &img, std::string &err);
+
+}  // namespace rfb

@@ -1,0 +1,226 @@
+"""Host-side mirror of the C ABI: Context / Nfa / scan().
+
+The reference's only "API" is the port list of `top` (Design/top.v:1-3) driven by the testbench
+(Simulation/testbench_BLK_Mem.sv): load a BRAM image, feed two byte traces, count accept pulses per
+state.  These classes expose exactly that through librfb200.so; all compute happens in the CUDA
+kernels -- there is no Python or CPU implementation of the scan anywhere in this package.
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+from ._lib import rfb_batch, rfb_nfa_info, rfb_result
+
+MATCH_DTYPE = np.dtype([("stream", "<u4"), ("pos", "<u4"), ("state", "<u4")])
+
+SCAN_SORT_RECORDS = 1
+SCAN_FORCE_WARP = 2
+SCAN_NO_COUNTS = 4
+SCAN_ASYNC = 8
+SCAN_ACCUMULATE = 16
+
+
+class RfbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"librfb200 error {code}: {msg}")
+        self.code = code
+
+
+def _check(rc, ctx=None):
+    if rc != 0:
+        msg = _lib.load().rfb_last_error(ctx).decode(errors="replace")
+        raise RfbError(rc, msg)
+
+
+def _info_dict(info):
+    return {n: int(getattr(info, n)) for n, _ in rfb_nfa_info._fields_ if n != "reserved"}
+
+
+# ---- host-only helpers (formats; no GPU) ---------------------------------------------------------
+def coe_parse(path):
+    """Block_Mem/*.coe -> uint32 entries[4*line+slot] (slot 0 = rd_bus[127:96], Design/FPGA.v:884)."""
+    L = _lib.load()
+    p = C.POINTER(C.c_uint32)()
+    n = C.c_size_t()
+    _check(L.rfb_coe_parse(str(path).encode(), C.byref(p), C.byref(n)))
+    out = np.ctypeslib.as_array(p, shape=(n.value,)).copy()
+    L.rfb_free(p)
+    return out
+
+
+def coe_write(path, entries, style=0):
+    e = np.ascontiguousarray(entries, dtype=np.uint32)
+    _check(_lib.load().rfb_coe_write(str(path).encode(), e.ctypes.data_as(C.POINTER(C.c_uint32)), e.size, style))
+
+
+def coe_detect_size(entries):
+    e = np.ascontiguousarray(entries, dtype=np.uint32)
+    return int(_lib.load().rfb_coe_detect_size(e.ctypes.data_as(C.POINTER(C.c_uint32)), e.size))
+
+
+def trace_load_mem(path):
+    """Simulation/*.mem ($readmemh text) -> uint8 array (testbench_BLK_Mem.sv:34-35)."""
+    L = _lib.load()
+    p = C.POINTER(C.c_uint8)()
+    n = C.c_size_t()
+    _check(L.rfb_trace_load_mem(str(path).encode(), C.byref(p), C.byref(n)))
+    out = np.ctypeslib.as_array(p, shape=(n.value,)).copy() if n.value else np.zeros(0, np.uint8)
+    L.rfb_free(p)
+    return out
+
+
+def trace_write_mem(path, data):
+    d = np.ascontiguousarray(data, dtype=np.uint8)
+    _check(_lib.load().rfb_trace_write_mem(str(path).encode(), d.ctypes.data_as(C.POINTER(C.c_uint8)), d.size))
+
+
+def tb_steps(trace_entries):
+    """Symbol steps the testbench executes on an M-entry trace: M-1 (testbench_BLK_Mem.sv:71-86)."""
+    return int(_lib.load().rfb_tb_steps(trace_entries))
+
+
+def image_check(entries, n_states=-1, sticky_words=0, bucket_bits=0):
+    """Host-only: build the execution image and verify it against the CSR for all (state, symbol)."""
+    e = np.ascontiguousarray(entries, dtype=np.uint32)
+    info = rfb_nfa_info()
+    _check(_lib.load().rfb_image_check(e.ctypes.data_as(C.POINTER(C.c_uint32)), e.size, n_states, sticky_words,
+                                       bucket_bits, C.byref(info)))
+    return _info_dict(info)
+
+
+# ---- GPU objects -----------------------------------------------------------------------------------
+class Context:
+    """One GPU (one process per GPU).  Fails loudly when no CUDA device is usable."""
+
+    def __init__(self, device_id=0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        _check(self._L.rfb_ctx_create(device_id, C.byref(h)))
+        self._h = h
+        self.device_id = device_id
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rfb_ctx_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def load_coe(self, path, n_states=-1):
+        h = C.c_void_p()
+        _check(self._L.rfb_nfa_load_coe(self._h, str(path).encode(), n_states, C.byref(h)), self._h)
+        return Nfa(self, h)
+
+    def nfa_from_entries(self, entries, n_states=-1):
+        e = np.ascontiguousarray(entries, dtype=np.uint32)
+        h = C.c_void_p()
+        _check(self._L.rfb_nfa_from_entries(self._h, e.ctypes.data_as(C.POINTER(C.c_uint32)), e.size, n_states,
+                                            C.byref(h)), self._h)
+        return Nfa(self, h)
+
+
+class ScanResult:
+    def __init__(self, counts, records, res):
+        self.counts = counts
+        self.records = records
+        self.n_matches = int(res.n_matches)
+        self.n_records = int(res.n_records)
+        self.n_dropped = int(res.n_dropped)
+        self.n_symbols = int(res.n_symbols)
+        self.n_rescanned = int(res.n_rescanned)
+        self.gpu_ms = float(res.gpu_ms)
+        self.n_launches = int(res.n_launches)
+
+
+class Nfa:
+    """A CSR NFA resident on the context's GPU (BRAM image + execution image)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self._L = ctx._L
+        self._h = handle
+        info = rfb_nfa_info()
+        _check(self._L.rfb_nfa_get_info(self._h, C.byref(info)))
+        self.info = _info_dict(info)
+        self.n_states = self.info["n_states"]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rfb_nfa_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def entries(self):
+        out = np.zeros(self.info["n_entries"], dtype=np.uint32)
+        _check(self._L.rfb_nfa_get_entries(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32)), out.size))
+        return out
+
+    # -- host buffers in, host results out (H2D + kernels + D2H inside the call) --
+    def scan(self, data, n_streams, n_steps=0, stride=0, offsets=None, steps=None, record_capacity=1 << 20,
+             flags=SCAN_SORT_RECORDS, stream_id_base=0, want_counts=True):
+        data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        b = rfb_batch()
+        b.data = data.ctypes.data if data.size else None
+        b.data_bytes = data.size
+        b.n_streams = n_streams
+        b.stride = stride
+        b.n_steps = n_steps
+        b.stream_id_base = stream_id_base
+        keep = [data]
+        if offsets is not None:
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
+            assert offsets.size == n_streams
+            b.offsets = offsets.ctypes.data
+            keep.append(offsets)
+        if steps is not None:
+            steps = np.ascontiguousarray(steps, dtype=np.uint32)
+            assert steps.size == n_streams
+            b.steps = steps.ctypes.data
+            keep.append(steps)
+        counts = np.zeros(self.n_states, dtype=np.uint64) if want_counts else None
+        records = np.zeros(record_capacity, dtype=MATCH_DTYPE)
+        r = rfb_result()
+        r.counts = counts.ctypes.data if want_counts else None
+        r.records = records.ctypes.data if record_capacity else None
+        r.record_capacity = record_capacity
+        _check(self._L.rfb_scan(self.ctx._h, self._h, C.byref(b), flags, C.byref(r)), self.ctx._h)
+        return ScanResult(counts, records[: r.n_records], r)
+
+    # -- device pointers in, device results out (for benchmarks: no PCIe in the timed region) --
+    def scan_device(self, data_ptr, data_bytes, n_streams, n_steps, stride, counts_ptr=None, records_ptr=None,
+                    record_capacity=0, flags=0, cuda_stream=None, offsets_ptr=None, steps_ptr=None,
+                    stream_id_base=0):
+        b = rfb_batch()
+        b.data = data_ptr
+        b.data_bytes = data_bytes
+        b.n_streams = n_streams
+        b.stride = stride
+        b.n_steps = n_steps
+        b.offsets = offsets_ptr
+        b.steps = steps_ptr
+        b.stream_id_base = stream_id_base
+        r = rfb_result()
+        r.counts = counts_ptr
+        r.records = records_ptr
+        r.record_capacity = record_capacity
+        _check(self._L.rfb_scan_device(self.ctx._h, self._h, C.byref(b), flags, cuda_stream, C.byref(r)), self.ctx._h)
+        return r
+
+    def collect(self, r):
+        _check(self._L.rfb_scan_collect(self.ctx._h, C.byref(r)), self.ctx._h)
+        return r

@@ -1,0 +1,237 @@
+"""GPU parity: the CUDA scan (through the C ABI) against the CPU oracle, bit-exact.
+
+Everything here needs a B200 (`-m gpu`).  Records and counts must be identical to oracle B, which
+tests/test_oracle.py pins against the cycle-level restatement of FPGA.v and SURVEY.md Appendix C.
+"""
+import numpy as np
+import pytest
+
+import regex_fpga_b200 as R
+from regex_fpga_b200 import workloads as WL
+from oracle import oracle_py as O
+from nfa_gen import build_entries, random_nfa, random_streams
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [("lane", R.SCAN_SORT_RECORDS), ("warp", R.SCAN_SORT_RECORDS | R.SCAN_FORCE_WARP)]
+
+
+def recs_tuple(r):
+    return list(zip(r["stream"].tolist(), r["pos"].tolist(), r["state"].tolist()))
+
+
+def check_against_oracle(nfa, E, n_states, data2d, n_steps, flags, stride=None, cap=1 << 20):
+    n_streams = data2d.shape[0]
+    stride = data2d.shape[1] if stride is None else stride
+    got = nfa.scan(data2d, n_streams, n_steps=n_steps, stride=stride, record_capacity=cap, flags=flags)
+    want = O.b_scan_many(E, n_states, data2d, n_streams, stride, n_steps, cap=cap)
+    assert got.n_matches == want["n_recs"]
+    assert np.array_equal(got.counts, want["counts"])
+    assert recs_tuple(got.records) == recs_tuple(want["recs"])
+    assert got.n_symbols == n_streams * n_steps
+    assert got.n_dropped == 0
+    return got
+
+
+@pytest.mark.parametrize("kernel,flags", KERNELS)
+@pytest.mark.parametrize("name", ["snort_16", "l7_filter"])
+def test_testbench_run_matches_golden(gpu_ctx, snort, l7, expected, name, kernel, flags):
+    """BASELINE configs 1-2: the committed testbench on the shipped trace pair (M = 200000)."""
+    rs = snort if name == "snort_16" else l7
+    nfa = gpu_ctx.nfa_from_entries(rs.entries)
+    assert nfa.n_states == rs.n_states
+    M = expected["tb_trace_entries"]
+    data = np.stack([rs.lo[:M], rs.hi[:M]])          # stream 0 = lo = input_char, 1 = hi (TB:56-57)
+    got = nfa.scan(data, 2, n_steps=R.tb_steps(M), stride=M, flags=flags)
+    exp = expected["rulesets"][name]["tb"]
+    for stream, key in ((0, "lo"), (1, "hi")):
+        ev = got.records[got.records["stream"] == stream]
+        assert [[int(p), int(s)] for p, s in zip(ev["pos"], ev["state"])] == exp[key]["events"]
+    want_counts = np.zeros(rs.n_states, np.uint64)
+    for key in ("lo", "hi"):
+        for s, c in exp[key]["counts"].items():
+            want_counts[int(s)] += c
+    assert np.array_equal(got.counts, want_counts)
+    assert got.n_matches == exp["lo"]["n_matches"] + exp["hi"]["n_matches"]
+    if kernel == "lane":
+        assert nfa.info["image_ok"] == 1 and got.n_rescanned == 0
+
+
+def test_l7_full_files(gpu_ctx, l7, expected):
+    """The l7 traces hold 262144 entries; the TB only consumes 200000."""
+    nfa = gpu_ctx.nfa_from_entries(l7.entries)
+    data = np.stack([l7.lo, l7.hi])
+    got = nfa.scan(data, 2, n_steps=l7.lo.size - 1, stride=l7.lo.size)
+    exp = expected["rulesets"]["l7_filter"]["full"]
+    assert got.n_matches == exp["lo"]["n_matches"] + exp["hi"]["n_matches"] == 13
+    ev = got.records[got.records["stream"] == 0]
+    assert [[int(p), int(s)] for p, s in zip(ev["pos"], ev["state"])] == exp["lo"]["events"]
+
+
+@pytest.mark.parametrize("kernel,flags", KERNELS)
+@pytest.mark.parametrize("mix", ["wmix", "whi", "uniform"])
+def test_packet_streams_match_oracle(gpu_ctx, snort, kernel, flags, mix):
+    """BASELINE config 3 shape (1500-byte packet streams) on a subsample the oracle finishes quickly."""
+    nfa = gpu_ctx.nfa_from_entries(snort.entries)
+    n = 3000 if kernel == "lane" else 600
+    data = WL.make_batch_numpy(mix, snort.lo, snort.hi, n, 1500, 1536)
+    got = check_against_oracle(nfa, snort.entries, snort.n_states, data, 1500, flags)
+    if mix != "uniform":
+        assert got.n_matches > 0
+
+
+def test_l7_packet_streams(gpu_ctx, l7):
+    nfa = gpu_ctx.nfa_from_entries(l7.entries)
+    data = WL.make_batch_numpy("wmix", l7.lo, l7.hi, 2000, 1500, 1536)
+    check_against_oracle(nfa, l7.entries, l7.n_states, data, 1500, R.SCAN_SORT_RECORDS)
+
+
+@pytest.mark.parametrize("seed", range(25))
+def test_random_nfas_both_kernels(gpu_ctx, seed):
+    rng = np.random.default_rng(7000 + seed)
+    (E, n), syms = random_nfa(rng, n_states=int(rng.integers(2, 400)), alphabet=int(rng.integers(2, 30)),
+                              p_sticky=float(rng.choice([0.0, 0.1, 0.4])), max_fanout=int(rng.integers(1, 4)))
+    nfa = gpu_ctx.nfa_from_entries(E, n)
+    length = int(rng.integers(1, 300))
+    data = random_streams(rng, syms, int(rng.integers(1, 200)), length)
+    for _, flags in KERNELS:
+        check_against_oracle(nfa, E, n, data, length, flags)
+
+
+def test_high_activity_overflows_to_warp_kernel(gpu_ctx):
+    """More simultaneously active transient states than the lane kernel's ring holds: those streams
+    must be re-run by the general kernel and still be bit-exact, with no double reports."""
+    n = 64
+    rows = [[(1, s) for s in range(1, n - 1)]]                       # 0 fans out to everything
+    for s in range(1, n - 1):
+        rows.append([(1, s + 1 if s + 1 < n - 1 else 1), (2, n - 1), (1, n - 1)])
+    rows.append([])                                                  # accept
+    E, ns = build_entries(rows)
+    nfa = gpu_ctx.nfa_from_entries(E, ns)
+    rng = np.random.default_rng(5)
+    data = rng.choice(np.array([1, 1, 1, 2, 3], np.uint8), size=(300, 200))
+    data[::3] = 3                                                    # a third of the streams stay quiet
+    got = check_against_oracle(nfa, E, ns, data, 200, R.SCAN_SORT_RECORDS)
+    assert got.n_rescanned > 0 and got.n_rescanned <= 200
+    check_against_oracle(nfa, E, ns, data, 200, R.SCAN_SORT_RECORDS | R.SCAN_FORCE_WARP)
+
+
+def test_ragged_offsets_and_empty_streams(gpu_ctx, snort):
+    nfa = gpu_ctx.nfa_from_entries(snort.entries)
+    rng = np.random.default_rng(11)
+    n = 500
+    steps = rng.integers(0, 700, size=n).astype(np.uint32)
+    steps[::17] = 0                                                  # empty streams
+    steps[5] = 1
+    offsets = np.zeros(n, np.uint64)
+    pos = 3                                                          # deliberately unaligned starts
+    for s in range(n):
+        offsets[s] = pos
+        pos += int(steps[s]) + int(rng.integers(0, 5))
+    buf = np.zeros(pos + 16, np.uint8)
+    src = np.concatenate([snort.hi, snort.lo])
+    for s in range(n):
+        o = int(rng.integers(0, src.size - 700))
+        buf[int(offsets[s]): int(offsets[s]) + int(steps[s])] = src[o: o + int(steps[s])]
+    for _, flags in KERNELS:
+        got = nfa.scan(buf, n, offsets=offsets, steps=steps, flags=flags, stream_id_base=1000)
+        want_counts = np.zeros(snort.n_states, np.uint64)
+        want = []
+        for s in range(n):
+            b = O.b_scan(snort.entries, snort.n_states, buf[int(offsets[s]):], int(steps[s]), stream_id=1000 + s)
+            want_counts += b["counts"]
+            want += recs_tuple(b["recs"])
+        assert np.array_equal(got.counts, want_counts)
+        assert recs_tuple(got.records) == want
+        assert got.n_symbols == int(steps.sum())
+    # zero streams / zero steps are legal and report nothing
+    got = nfa.scan(np.zeros(16, np.uint8), 0, n_steps=10, stride=10)
+    assert got.n_matches == 0 and got.n_symbols == 0
+    got = nfa.scan(np.zeros(64, np.uint8), 4, n_steps=0, stride=16)
+    assert got.n_matches == 0 and got.n_symbols == 0
+
+
+def test_record_buffer_overflow_is_counted(gpu_ctx, snort):
+    nfa = gpu_ctx.nfa_from_entries(snort.entries)
+    data = WL.make_batch_numpy("whi", snort.lo, snort.hi, 512, 1500, 1536)
+    full = nfa.scan(data, 512, n_steps=1500, stride=1536)
+    assert full.n_matches > 200
+    small = nfa.scan(data, 512, n_steps=1500, stride=1536, record_capacity=100)
+    assert small.n_matches == full.n_matches and small.n_records == 100
+    assert small.n_dropped == full.n_matches - 100
+    assert np.array_equal(small.counts, full.counts)                 # counts never depend on capacity
+    allrec = set(recs_tuple(full.records))
+    assert all(r in allrec for r in recs_tuple(small.records))
+    none = nfa.scan(data, 512, n_steps=1500, stride=1536, record_capacity=0)
+    assert none.n_records == 0 and none.n_dropped == full.n_matches
+    assert np.array_equal(none.counts, full.counts)
+
+
+def test_accept_start_state_and_tiny_nfas(gpu_ctx):
+    E, n = build_entries([[]])                                       # size 1: state 0 accepts at step 0 only
+    nfa = gpu_ctx.nfa_from_entries(E, n)
+    data = np.zeros((3, 8), np.uint8)
+    for _, flags in KERNELS:
+        got = nfa.scan(data, 3, n_steps=8, stride=8, flags=flags)
+        assert recs_tuple(got.records) == [(0, 0, 0), (1, 0, 0), (2, 0, 0)]
+    E, n = build_entries([[(7, 0), (7, 1)], []])                     # 0 loops on 7 and feeds accept 1
+    nfa = gpu_ctx.nfa_from_entries(E, n)
+    d = np.full((2, 2000), 7, np.uint8)
+    d[1, 1000] = 8
+    for _, flags in KERNELS:
+        got = check_against_oracle(nfa, E, n, d, 2000, flags)
+        assert got.counts[1] == 1999 + 1000
+
+
+def test_device_resident_scan_matches_host_scan(gpu_ctx, snort):
+    """rfb_scan_device (the entry point bench.py times) against rfb_scan on the same batch."""
+    import torch
+    nfa = gpu_ctx.nfa_from_entries(snort.entries)
+    n = 4096
+    host = WL.make_batch_numpy("wmix", snort.lo, snort.hi, n, 1500, 1536)
+    dev = WL.make_batch_torch("wmix", snort.lo, snort.hi, n, "cuda:0", 1500, 1536)
+    assert np.array_equal(dev.cpu().numpy(), host)                   # generators agree byte for byte
+    counts = torch.zeros(snort.n_states, dtype=torch.int64, device="cuda:0")
+    cap = 1 << 16
+    recs = torch.zeros(cap * 3, dtype=torch.int32, device="cuda:0")
+    r = nfa.scan_device(dev.data_ptr(), dev.numel(), n, 1500, 1536, counts.data_ptr(), recs.data_ptr(), cap,
+                        cuda_stream=torch.cuda.current_stream().cuda_stream)
+    ref = nfa.scan(host, n, n_steps=1500, stride=1536)
+    assert r.n_matches == ref.n_matches and r.n_symbols == n * 1500
+    assert np.array_equal(counts.cpu().numpy().astype(np.uint64), ref.counts)
+    got = recs.cpu().numpy().view(np.uint32).reshape(-1, 3)[: r.n_records]
+    got = sorted(map(tuple, got.tolist()))
+    assert got == recs_tuple(ref.records)
+
+
+def test_large_batch_properties(gpu_ctx, snort):
+    """Full-size-shaped batch (256K streams here; bench runs 1M): size-independent properties --
+    counts are additive over any partition of the streams, independent of stream order, and the lane
+    and warp kernels agree."""
+    import torch
+    nfa = gpu_ctx.nfa_from_entries(snort.entries)
+    n = 1 << 18
+    dev = WL.make_batch_torch("wmix", snort.lo, snort.hi, n, "cuda:0", 1500, 1536)
+
+    def run(t, flags=0):
+        c = torch.zeros(snort.n_states, dtype=torch.int64, device="cuda:0")
+        r = nfa.scan_device(t.data_ptr(), t.numel(), t.shape[0], 1500, 1536, c.data_ptr(), None, 0, flags=flags)
+        return c.cpu().numpy(), r.n_matches
+
+    c_all, m_all = run(dev)
+    c_a, m_a = run(dev[: n // 3].contiguous())
+    c_b, m_b = run(dev[n // 3:].contiguous())
+    assert m_all == m_a + m_b and np.array_equal(c_all, c_a + c_b) and m_all == int(c_all.sum())
+    perm = torch.randperm(n, device="cuda:0", generator=torch.Generator("cuda:0").manual_seed(1))
+    c_p, m_p = run(dev[perm].contiguous())
+    assert m_p == m_all and np.array_equal(c_p, c_all)
+    sub = dev[: 1 << 14].contiguous()
+    c_l, _ = run(sub)
+    c_w, _ = run(sub, R.SCAN_FORCE_WARP)
+    assert np.array_equal(c_l, c_w)
+    # and a strided subsample against the oracle
+    idx = np.arange(0, n, n // 512)[:512]
+    host = dev[torch.from_numpy(idx).to("cuda:0")].cpu().numpy()
+    want = O.b_scan_many(snort.entries, snort.n_states, host, 512, 1536, 1500, want_recs=False)
+    c_s, _ = run(torch.from_numpy(host).to("cuda:0"))
+    assert np.array_equal(c_s.astype(np.uint64), want["counts"])

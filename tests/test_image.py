@@ -1,0 +1,70 @@
+"""Host logic of the load-time re-indexing (csrc/image.cpp): rfb_image_check builds the lane kernel's
+execution image and proves it equivalent to the CSR for every (state, symbol) pair."""
+import numpy as np
+import pytest
+
+import regex_fpga_b200 as R
+from nfa_gen import build_entries, random_nfa
+
+
+@pytest.mark.parametrize("sticky_words,bucket_bits", [(0, 0), (1, 3), (2, 4), (1, 2)])
+def test_shipped_rulesets_verify(snort, l7, sticky_words, bucket_bits):
+    for rs in (snort, l7):
+        info = R.image_check(rs.entries, -1, sticky_words, bucket_bits)
+        assert info["image_ok"] == 1
+        assert info["n_states"] == rs.n_states
+        assert info["image_bytes"] < 190 * 1024
+        assert info["n_slots"] <= 0x8000
+
+
+def test_shipped_ruleset_shapes(snort, l7):
+    s = R.image_check(snort.entries)
+    assert (s["n_states"], s["n_transitions"], s["n_accepting"]) == (9514, 79856, 536)
+    assert s["n_sticky"] >= 65          # 23 full + 42 all-but-newline self-loop states
+    f = R.image_check(l7.entries)
+    assert (f["n_states"], f["n_transitions"], f["n_accepting"]) == (2794, 124977, 204)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_nfas_verify(seed):
+    rng = np.random.default_rng(seed)
+    (E, n), _ = random_nfa(rng, n_states=int(rng.integers(2, 300)), alphabet=int(rng.integers(2, 40)),
+                           p_sticky=float(rng.choice([0.0, 0.1, 0.5])), max_fanout=int(rng.integers(1, 4)))
+    for sw, bb in ((0, 0), (1, 1), (2, 5)):
+        info = R.image_check(E, n, sw, bb)
+        assert info["image_ok"] == 1 and info["n_states"] == n
+
+
+def test_more_sticky_candidates_than_mask_bits():
+    """> 128 self-looping states: the surplus must stay correct as ordinary (class-edge) states."""
+    rows = [[(1, s) for s in range(1, 200)]]
+    for s in range(1, 200):
+        rows.append([(c, s) for c in range(256) if c != s % 7] + [(2, (s % 198) + 1)])
+    E, n = build_entries(rows)
+    info = R.image_check(E, n)
+    assert info["image_ok"] == 1 and info["n_sticky"] == 128 and info["sticky_words"] == 2
+
+
+def test_invalid_images_are_rejected():
+    E, n = build_entries([[(1, 1)], []])
+    bad = E.copy()
+    bad[n + 1] = (1 << 24) | 5            # target >= n_states
+    with pytest.raises(R.RfbError) as e:
+        R.image_check(bad, n)
+    assert e.value.code == -4
+    bad = E.copy()
+    bad[1] = 3
+    bad[2] = 1                            # row_ptr decreasing
+    with pytest.raises(R.RfbError):
+        R.image_check(bad, n)
+    with pytest.raises(R.RfbError):
+        R.image_check(np.array([1, 2, 3, 4], np.uint32), -1)   # row_ptr[0] != 0: size not detectable
+
+
+def test_too_large_for_shared_memory_falls_to_warp_kernel():
+    """40000 branching states do not fit the 15-bit id space: image_ok = 0, NFA still valid."""
+    n = 40000
+    rows = [[(1, (s + 1) % n or 1), (2, (s + 7) % n or 1)] for s in range(n)]
+    E, n = build_entries(rows)
+    info = R.image_check(E, n)
+    assert info["image_ok"] == 0 and info["n_states"] == n
