@@ -224,6 +224,7 @@ int rfb_image_check(const uint32_t *entries, size_t n_entries, int64_t n_states,
     ImageOptions opt = default_image_options();
     if (sticky_words > 0) opt.sticky_words = sticky_words;
     if (bucket_bits > 0) opt.bucket_bits = bucket_bits;
+    else if (!std::getenv("RFB_BUCKET_BITS")) opt.bucket_bits = -1;
     rc = image_build(host, opt, img, err);
     if (rc) return fail(nullptr, rc, err);
     fill_info(host, img, info);

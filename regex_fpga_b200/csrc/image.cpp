@@ -50,7 +50,7 @@ inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
 }  // namespace
 
-int image_build(const Nfa &nfa, const ImageOptions &opt, Image &img, std::string &err) {
+static int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::string &err) {
     img = Image();
     const uint32_t N = nfa.n_states;
     const uint32_t *rp = nfa.row_ptr();
@@ -103,29 +103,40 @@ int image_build(const Nfa &nfa, const ImageOptions &opt, Image &img, std::string
     int bb = opt.bucket_bits;
     uint32_t n_branch = 0;
     for (uint32_t s = 0; s < N; s++) n_branch += (sticky_bit[s] < 0 && !is_single(s));
-    if (bb < 0) bb = 3;
+    if (bb < 0) bb = 4;
     if (bb > 6) bb = 6;
     const uint32_t NB = 1u << bb;
     for (uint32_t s = 0; s < N; s++)
         if (sticky_bit[s] < 0 && !is_single(s)) { img.id_of_orig[s] = next_id; next_id += NB; }
     const uint32_t chain_base = next_id;
 
-    // ---- bucket hash: pick the (mul, shift) with the fewest multi-edge buckets -----------------------
+    // ---- bucket hash: pick (mul, shift) minimising the expected table lookups per visit -------------
+    // A visit with symbol c costs 1 lookup when bucket(c) holds <= 1 edge, 1 + n when it holds n >= 2
+    // (indirection + chain).  Symbols that appear on some edge of the state are what the traffic that
+    // activated the state tends to continue with, so they carry the weight; all others share weight 1.
     auto bucket_of = [&](uint32_t c, uint32_t mul, uint32_t sh) { return ((c * mul) >> sh) & (NB - 1); };
     uint32_t best_mul = 1, best_sh = 0;
-    uint64_t best_cost = ~0ull;
+    double best_cost = 1e300;
+    std::vector<uint32_t> branchers;
+    for (uint32_t s = 0; s < N; s++) if (sticky_bit[s] < 0 && !is_single(s)) branchers.push_back(s);
     for (uint32_t mul = 1; mul < 64; mul += 2)
         for (uint32_t sh = 0; sh < 8; sh++) {
-            uint64_t cost = 0;
-            for (uint32_t s = 0; s < N && cost < best_cost; s++) {
-                if (sticky_bit[s] >= 0 || is_single(s)) continue;
+            double cost = 0;
+            for (uint32_t s : branchers) {
+                if (cost >= best_cost) break;
                 uint32_t per_bucket[64] = {0};
+                SymSet used;
                 for (const Edge &e : edges[s]) {
                     uint64_t seen = 0;
-                    for (uint32_t c : e.syms.members()) seen |= 1ull << bucket_of(c, mul, sh);
+                    for (uint32_t c : e.syms.members()) { seen |= 1ull << bucket_of(c, mul, sh); used.set(c); }
                     for (uint32_t q = 0; q < NB; q++) per_bucket[q] += (seen >> q) & 1;
                 }
-                for (uint32_t q = 0; q < NB; q++) if (per_bucket[q] > 1) cost += 1 + per_bucket[q];
+                const int n_used = used.count();
+                const double w_used = 1.0 / n_used, w_other = n_used < 256 ? 1.0 / (256 - n_used) : 0.0;
+                for (uint32_t c = 0; c < 256; c++) {
+                    const uint32_t n = per_bucket[bucket_of(c, mul, sh)];
+                    cost += (used.has(c) ? w_used : w_other) * (n <= 1 ? 1.0 : 1.0 + n);
+                }
             }
             if (cost < best_cost) { best_cost = cost; best_mul = mul; best_sh = sh; }
         }
@@ -246,6 +257,19 @@ int image_build(const Nfa &nfa, const ImageOptions &opt, Image &img, std::string
         if (rc) { img.ok = false; return rc; }
     }
     return RFB_OK;
+}
+
+// bucket_bits < 0: the most buckets (up to 16 per branching state) whose tables still fit.
+int image_build(const Nfa &nfa, const ImageOptions &opt, Image &img, std::string &err) {
+    if (opt.bucket_bits >= 0) return image_build_one(nfa, opt, img, err);
+    ImageOptions o = opt;
+    int rc = RFB_OK;
+    for (int bb = 4; bb >= 1; bb--) {
+        o.bucket_bits = bb;
+        rc = image_build_one(nfa, o, img, err);
+        if (rc != RFB_OK || img.ok) return rc;
+    }
+    return rc;
 }
 
 // The kernel's semantics, on the host.  Keep in lock-step with scan_lane.cu.

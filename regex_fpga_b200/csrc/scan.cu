@@ -89,45 +89,130 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     const uint32_t gbase = h.gbase, nsb = h.nsb, hmul = h.hash_mul, hsh = h.hash_shift;
     const uint32_t nbm = (1u << h.bucket_bits) - 1u;
     constexpr uint32_t MSTRIDE = 32u * W;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
 
-    // ---- per-lane stream state -------------------------------------------------------------------
-    uint64_t P[W], Pn[W];
-    uint32_t head = 0, rd = 0, ncur = 0, nnew = 0, flo = 0, fhi = 0;
-    uint32_t c = 0, hc = 0, idx = 0, k = 0, nsteps = 0, sid = 0;
-    bool walking = false, ovf = false, have = false;
-    uint64_t blo = 0, bhi = 0, plo = 0, phi = 0;  // current / prefetched 16 input bytes
-    uint32_t bufn = 0;
-    const uint8_t *nextp = nullptr, *endp = nullptr;
-#pragma unroll
-    for (int w = 0; w < W; w++) { P[w] = 0; Pn[w] = 0; }
-
-    auto push = [&](uint32_t t) {
-        if (t < nsb) {
-            const uint64_t bit = 1ull << (t & 63);
-            if (W == 1 || t < 64) Pn[0] |= bit; else Pn[W - 1] |= bit;
-            return;
-        }
-        const uint32_t bit = 1u << (t & 31);
-        const bool hi = (t & 32) != 0;
-        const uint32_t f = hi ? fhi : flo;
-        bool dup = false;
-        if (f & bit) {  // possible duplicate: exact check against this step's new entries
-            for (uint32_t j = 0; j < nnew; j++)
-                if (list[((head + ncur + j) & (LANE_CAP - 1)) * LANE_THREADS] == t) { dup = true; break; }
-        }
-        if (!dup) {
-            if (ncur - rd + nnew >= (uint32_t)LANE_CAP) { ovf = true; return; }
-            list[((head + ncur + nnew) & (LANE_CAP - 1)) * LANE_THREADS] = (uint16_t)t;
-            nnew++;
-            if (hi) fhi |= bit; else flo |= bit;
-        }
-    };
-
+    // A warp takes 32 consecutive streams at a time and steps them in lock-step, one symbol per
+    // iteration of the k loop, so that the per-symbol bookkeeping runs with all 32 lanes converged.
     for (;;) {
-        if (!walking && rd == ncur) {
-            // ================= end of symbol step k (or no stream yet) =================
-            if (have) {
-                // sticky states: P' = (P & K[c]) | entered ; injections from P & M[c]
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(&out.g->next_stream, 32u);
+        base = __shfl_sync(FULL, base, 0);
+        if (base >= batch.n_streams) break;
+        const uint32_t sid = base + lane;
+        const bool valid = sid < batch.n_streams;
+        const uint32_t nsteps = valid ? (batch.steps ? batch.steps[sid] : batch.n_steps) : 0u;
+        const uint32_t maxsteps = __reduce_max_sync(FULL, nsteps);
+
+        // ---- per-lane stream state ----
+        uint64_t P[W], Pn[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) { P[w] = 0; Pn[w] = 0; }
+        uint32_t head = 0, rd = 0, ncur = 0, nnew = 0, flo = 0, fhi = 0;
+        bool ovf = false;
+        uint32_t ovf_at = 0;
+        if (nsteps) {
+            if (h.start_id < nsb) {                                                   // Design/FPGA.v:146-147
+                if (W == 1 || h.start_id < 64) P[0] |= 1ull << (h.start_id & 63); else P[W - 1] |= 1ull << (h.start_id & 63);
+            } else { list[0] = (uint16_t)h.start_id; ncur = 1; }
+        }
+        // input: aligned 16-byte chunks kept in registers, the first one shifted to the stream's first byte
+        uint64_t blo = 0, bhi = 0, plo = 0, phi = 0;
+        uint32_t bufn = 16;
+        const uint8_t *nextp = nullptr, *endp = nullptr;
+        if (nsteps) {
+            const uint8_t *sp = stream_ptr(batch, sid);
+            endp = sp + nsteps;
+            const uint8_t *b16 = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15);
+            const uint32_t off = (uint32_t)(sp - b16);
+            uint4 v = __ldg(reinterpret_cast<const uint4 *>(b16));
+            blo = (uint64_t)v.x | ((uint64_t)v.y << 32);
+            bhi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+            const uint32_t sh = off * 8;
+            if (sh >= 64) { blo = bhi >> (sh - 64); bhi = 0; }
+            else if (sh) { blo = (blo >> sh) | (bhi << (64 - sh)); bhi >>= sh; }
+            bufn = 16 - off;
+            nextp = b16 + 16;
+            if (nextp < endp) {
+                v = __ldg(reinterpret_cast<const uint4 *>(nextp));
+                plo = (uint64_t)v.x | ((uint64_t)v.y << 32);
+                phi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+            }
+            nextp += 16;
+        }
+
+        auto push = [&](uint32_t t) {
+            if (t < nsb) {
+                const uint64_t bit = 1ull << (t & 63);
+                if (W == 1 || t < 64) Pn[0] |= bit; else Pn[W - 1] |= bit;
+                return;
+            }
+            const uint32_t bit = 1u << (t & 31);
+            const bool hi = (t & 32) != 0;
+            const uint32_t f = hi ? fhi : flo;
+            bool dup = false;
+            if (f & bit) {  // possible duplicate: exact check against this step's new entries
+                for (uint32_t j = 0; j < nnew; j++)
+                    if (list[((head + ncur + j) & (LANE_CAP - 1)) * LANE_THREADS] == t) { dup = true; break; }
+            }
+            if (!dup) {
+                if (ncur - rd + nnew >= (uint32_t)LANE_CAP) { ovf = true; return; }
+                list[((head + ncur + nnew) & (LANE_CAP - 1)) * LANE_THREADS] = (uint16_t)t;
+                nnew++;
+                if (hi) fhi |= bit; else flo |= bit;
+            }
+        };
+
+        for (uint32_t k = 0; k < maxsteps; k++) {
+            const bool act = k < nsteps && !ovf;
+            // ---- next symbol ----
+            if (bufn == 0) {
+                blo = plo; bhi = phi; bufn = 16;
+                if (nextp < endp) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(nextp));
+                    plo = (uint64_t)v.x | ((uint64_t)v.y << 32);
+                    phi = (uint64_t)v.z | ((uint64_t)v.w << 32);
+                }
+                nextp += 16;
+            }
+            const uint32_t c = (uint32_t)blo & 0xFFu;
+            blo = (blo >> 8) | (bhi << 56);
+            bhi >>= 8;
+            bufn--;
+            const uint32_t hc = ((c * hmul) >> hsh) & nbm;
+
+            // ---- transient states of S_k: one table lookup per lane per iteration ----
+            bool walking = false;
+            uint32_t idx = 0;
+            bool work = act && rd < ncur;
+            while (__any_sync(FULL, work)) {
+                if (work) {
+                    if (!walking) {
+                        const uint32_t u = list[((head + rd) & (LANE_CAP - 1)) * LANE_THREADS];
+                        rd++;
+                        idx = u + (u >= gbase ? hc : 0u);
+                    }
+                    const uint32_t e = tab[idx];
+                    const uint32_t a = e & 0xFFu, b = (e >> 8) & 0xFFu, t = (e >> 16) & 0x7FFFu;
+                    bool hit = false, redirect = false;
+                    if (a <= b) hit = (c == a) | (c == b);
+                    else if (a == 0xFFu) {
+                        if (b == CODE_ACCEPT) emit_match(out, sid + batch.stream_id_base, k, nfa.orig_of_id[idx]);
+                        else if (b == CODE_INDIRECT) redirect = true;
+                    } else {
+                        const uint32_t n = (0xFEu - a) * 253u + b;
+                        hit = (memb[n * 8 + (c >> 5)] >> (c & 31)) & 1u;
+                    }
+                    if (hit && !ovf) push(t);
+                    if (redirect) { idx = t; walking = true; }
+                    else if (e & TAB_MORE) { idx++; walking = true; }
+                    else walking = false;
+                    work = walking || rd < ncur;
+                }
+            }
+
+            // ---- sticky states: P' = (P & K[c]) | entered ; injections from P & M[c] ----
+            if (act) {
                 const uint8_t *mrow = mask + c * MSTRIDE;
                 bool attn = false;
 #pragma unroll
@@ -140,9 +225,9 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                         uint64_t im = P[w] & M;
                         P[w] &= K;
                         while (im) {
-                            const uint32_t b = (uint32_t)__ffsll((long long)im) - 1u;
+                            const uint32_t bpos = (uint32_t)__ffsll((long long)im) - 1u;
                             im &= im - 1;
-                            const uint32_t x = inj[(w * 64 + b) * 256 + c];
+                            const uint32_t x = inj[(w * 64 + bpos) * 256 + c];
                             if (ovf) continue;
                             if (x < 0x8000u) push(x);
                             else if (x != 0xFFFFu) {
@@ -154,91 +239,20 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                 }
 #pragma unroll
                 for (int w = 0; w < W; w++) { P[w] |= Pn[w]; Pn[w] = 0; }
+                // current <= next (Design/FPGA.v:733-737)
                 head += ncur; rd = 0; ncur = nnew; nnew = 0; flo = 0; fhi = 0;
-                k++;
-                if (k == nsteps || ovf) {
-                    if (ovf && k < nsteps) {  // the general kernel reports everything from step k on
-                        unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
-                        out.rescan[slot] = make_uint2(sid, k);
-                    }
-                    have = false;
-                }
+                if (ovf) ovf_at = k + 1;   // S_k was fully examined; the general kernel reports from step k+1 on
             }
-            if (!have) {
-                // ---- fetch the next stream ----
-                for (;;) {
-                    sid = atomicAdd(&out.g->next_stream, 1u);
-                    if (sid >= batch.n_streams) break;
-                    nsteps = batch.steps ? batch.steps[sid] : batch.n_steps;
-                    if (nsteps != 0) break;
-                }
-                if (sid >= batch.n_streams) break;  // this lane is done
-                if (batch.steps) atomicAdd(&out.g->n_symbols, (unsigned long long)nsteps);
+        }
+        if (ovf && ovf_at < nsteps) {
+            const unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
+            out.rescan[slot] = make_uint2(sid, ovf_at);
+        }
+        if (batch.steps) {
+            unsigned long long tot = nsteps;
 #pragma unroll
-                for (int w = 0; w < W; w++) { P[w] = 0; Pn[w] = 0; }
-                head = 0; rd = 0; ncur = 0; nnew = 0; flo = 0; fhi = 0; k = 0; ovf = false; have = true;
-                if (h.start_id < nsb) {                                                   // Design/FPGA.v:146-147
-                    if (W == 1 || h.start_id < 64) P[0] |= 1ull << (h.start_id & 63); else P[W - 1] |= 1ull << (h.start_id & 63);
-                }
-                else { list[0] = (uint16_t)h.start_id; ncur = 1; }
-                // input: aligned 16-byte chunks, first one shifted to the stream's first byte
-                const uint8_t *sp = stream_ptr(batch, sid);
-                endp = sp + nsteps;
-                const uint8_t *base = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15);
-                const uint32_t off = (uint32_t)(sp - base);
-                uint4 v = __ldg(reinterpret_cast<const uint4 *>(base));
-                blo = (uint64_t)v.x | ((uint64_t)v.y << 32);
-                bhi = (uint64_t)v.z | ((uint64_t)v.w << 32);
-                const uint32_t sh = off * 8;
-                if (sh >= 64) { blo = bhi >> (sh - 64); bhi = 0; }
-                else if (sh) { blo = (blo >> sh) | (bhi << (64 - sh)); bhi >>= sh; }
-                bufn = 16 - off;
-                nextp = base + 16;
-                if (nextp < endp) {
-                    v = __ldg(reinterpret_cast<const uint4 *>(nextp));
-                    plo = (uint64_t)v.x | ((uint64_t)v.y << 32);
-                    phi = (uint64_t)v.z | ((uint64_t)v.w << 32);
-                }
-                nextp += 16;
-            }
-            // ---- next symbol ----
-            if (bufn == 0) {
-                blo = plo; bhi = phi; bufn = 16;
-                if (nextp < endp) {
-                    uint4 v = __ldg(reinterpret_cast<const uint4 *>(nextp));
-                    plo = (uint64_t)v.x | ((uint64_t)v.y << 32);
-                    phi = (uint64_t)v.z | ((uint64_t)v.w << 32);
-                }
-                nextp += 16;
-            }
-            c = (uint32_t)blo & 0xFFu;
-            blo = (blo >> 8) | (bhi << 56);
-            bhi >>= 8;
-            bufn--;
-            hc = ((c * hmul) >> hsh) & nbm;
-        }
-        if (!walking && rd < ncur) {
-            const uint32_t u = list[((head + rd) & (LANE_CAP - 1)) * LANE_THREADS];
-            rd++;
-            idx = u + (u >= gbase ? hc : 0u);
-            walking = true;
-        }
-        if (walking) {
-            const uint32_t e = tab[idx];
-            const uint32_t a = e & 0xFFu, b = (e >> 8) & 0xFFu, t = (e >> 16) & 0x7FFFu;
-            bool hit = false, redirect = false;
-            if (a <= b) hit = (c == a) | (c == b);
-            else if (a == 0xFFu) {
-                if (b == CODE_ACCEPT) emit_match(out, sid + batch.stream_id_base, k, nfa.orig_of_id[idx]);
-                else if (b == CODE_INDIRECT) redirect = true;
-            } else {
-                const uint32_t n = (0xFEu - a) * 253u + b;
-                hit = (memb[n * 8 + (c >> 5)] >> (c & 31)) & 1u;
-            }
-            if (hit && !ovf) push(t);
-            if (redirect) idx = t;
-            else if (e & TAB_MORE) idx++;
-            else walking = false;
+            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+            if (lane == 0) atomicAdd(&out.g->n_symbols, tot);
         }
     }
 }

@@ -1,0 +1,121 @@
+// image_stats.cpp -- developer diagnostic (NOT part of the product library or of any test): replays
+// streams through the execution-image tables on the host and counts what the lane kernel would do per
+// symbol (list entries, table lookups, indirections, class tests, pushes, sticky "attention" events),
+// including the per-32-stream maximum that bounds a lock-step warp.  Used to size kernel design choices.
+//   g++ -O2 -std=c++17 -I regex_fpga_b200/csrc tools/image_stats.cpp regex_fpga_b200/csrc/{image,nfa,formats}.cpp -o /tmp/image_stats
+//   /tmp/image_stats <coe> <lo.mem> <hi.mem> [n_streams] [bucket_bits] [sticky_words]
+#include "host.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <set>
+#include <vector>
+using namespace rfb;
+
+static uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+struct Stats { double entries = 0, lookups = 0, indirect = 0, cls = 0, pushes = 0, attn = 0, inj = 0, sticky = 0, symbols = 0, maxlist = 0; };
+
+int main(int argc, char **argv) {
+    if (argc < 4) return 1;
+    std::vector<uint32_t> E; std::vector<uint8_t> lo, hi; std::string err;
+    if (coe_parse_file(argv[1], E, err) || mem_parse_file(argv[2], lo, err) || mem_parse_file(argv[3], hi, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
+    int n_streams = argc > 4 ? atoi(argv[4]) : 1024;
+    ImageOptions opt; if (argc > 5) opt.bucket_bits = atoi(argv[5]); if (argc > 6) opt.sticky_words = atoi(argv[6]);
+    Nfa nfa; Image img;
+    if (nfa_from_entries(E.data(), E.size(), -1, nfa, err) || image_build(nfa, opt, img, err) || !img.ok) { fprintf(stderr, "image: %s %s\n", err.c_str(), img.why_not.c_str()); return 1; }
+    const ImageHeader &h = img.h;
+    const uint32_t *tab = (const uint32_t *)&img.blob[h.off_tab];
+    const uint16_t *inj = (const uint16_t *)&img.blob[h.off_inj];
+    const uint32_t *memb = (const uint32_t *)&img.blob[h.off_memb];
+    const uint16_t *tlist = (const uint16_t *)&img.blob[h.off_tlist];
+    const uint32_t W = h.sticky_words, ms = 32 * W, L = 1500;
+    printf("image: slots %u gbase %u nsb %u W %u bucket_bits %u bytes %u sets %u sticky %u\n", h.n_slots, h.gbase, h.nsb, W, h.bucket_bits, h.blob_bytes, h.n_sets, img.n_sticky);
+    Stats st[2];
+    std::vector<double> visits(h.n_slots,0), vlook(h.n_slots,0);
+    std::vector<std::vector<uint32_t>> per_sym_lookups(n_streams, std::vector<uint32_t>(L));
+    std::vector<std::vector<uint32_t>> per_sym_entries(n_streams, std::vector<uint32_t>(L));
+    for (int j = 0; j < n_streams; j++) {
+        const std::vector<uint8_t> &src = (j & 1) ? hi : lo;
+        uint64_t off = splitmix64(0x5EED0001ull ^ (uint64_t)j) % (std::min(lo.size(), hi.size()) - L + 1);
+        Stats &s = st[j & 1];
+        uint64_t P[2] = {0, 0};
+        std::vector<uint32_t> cur, nxt;
+        if (h.start_id < h.nsb) P[h.start_id >> 6] |= 1ull << (h.start_id & 63); else cur.push_back(h.start_id);
+        for (uint32_t k = 0; k < L; k++) {
+            uint32_t c = src[off + k], hc = ((c * h.hash_mul) >> h.hash_shift) & ((1u << h.bucket_bits) - 1);
+            uint64_t Pn[2] = {0, 0};
+            std::set<uint32_t> seen;
+            uint32_t lk = 0;
+            auto push = [&](uint32_t t) { s.pushes++; if (t < h.nsb) Pn[t >> 6] |= 1ull << (t & 63); else if (seen.insert(t).second) nxt.push_back(t); };
+            s.entries += cur.size(); per_sym_entries[j][k] = cur.size();
+            s.maxlist = std::max<double>(s.maxlist, cur.size());
+            for (uint32_t u : cur) {
+                uint32_t idx = u + (u >= h.gbase ? hc : 0); uint32_t lk0 = lk; visits[u]++;
+                for (;;) {
+                    uint32_t e = tab[idx]; lk++;
+                    uint32_t a = e & 0xFF, b = (e >> 8) & 0xFF, t = (e >> 16) & 0x7FFF;
+                    if (a <= b) { if (c == a || c == b) push(t); }
+                    else if (a == 0xFF) { if (b == CODE_INDIRECT) { s.indirect++; idx = t; continue; } }
+                    else { s.cls++; uint32_t n = (0xFE - a) * 253 + b; if ((memb[n * 8 + (c >> 5)] >> (c & 31)) & 1) push(t); }
+                    if (!(e & TAB_MORE)) break;
+                    idx++;
+                }
+                vlook[u] += lk - lk0;
+            }
+            s.lookups += lk; per_sym_lookups[j][k] = lk;
+            const uint64_t *A = (const uint64_t *)&img.blob[h.off_mask + c * ms];
+            const uint64_t *K = (const uint64_t *)&img.blob[h.off_mask + c * ms + 16];
+            const uint64_t *M = K + W;
+            bool attn = false;
+            for (uint32_t w = 0; w < W; w++) { attn |= (P[w] & A[w]) != 0; s.sticky += __builtin_popcountll(P[w]); }
+            if (attn) {
+                s.attn++;
+                for (uint32_t w = 0; w < W; w++) {
+                    uint64_t im = P[w] & M[w]; P[w] &= K[w];
+                    while (im) {
+                        uint32_t b = __builtin_ctzll(im); im &= im - 1; s.inj++;
+                        uint32_t x = inj[(w * 64 + b) * 256 + c];
+                        if (x < 0x8000) push(x); else if (x != 0xFFFF) for (uint32_t q = x & 0x7FFF;; q++) { push(tlist[q] & 0x7FFF); if (!(tlist[q] & 0x8000)) break; }
+                    }
+                }
+            }
+            for (uint32_t w = 0; w < W; w++) P[w] |= Pn[w];
+            cur.swap(nxt); nxt.clear(); s.symbols++;
+        }
+    }
+    for (int t = 0; t < 2; t++) {
+        Stats &s = st[t];
+        printf("%s: per symbol: entries %.3f lookups %.3f indirect %.3f class %.3f pushes %.3f attn %.3f inj %.3f sticky %.2f maxlist %.0f\n", t ? "hi" : "lo",
+               s.entries / s.symbols, s.lookups / s.symbols, s.indirect / s.symbols, s.cls / s.symbols, s.pushes / s.symbols, s.attn / s.symbols, s.inj / s.symbols, s.sticky / s.symbols, s.maxlist);
+    }
+    {
+        std::vector<uint32_t> order(h.n_slots); for (uint32_t i = 0; i < h.n_slots; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return vlook[a] > vlook[b]; });
+        double tv = 0, tl = 0; for (uint32_t i = 0; i < h.n_slots; i++) { tv += visits[i]; tl += vlook[i]; }
+        for (int r = 0; r < 14; r++) {
+            uint32_t u = order[r];
+            printf("  id %5u orig %5u visits %5.2f%% lookups %5.2f%% (%.2f/visit) %s row:", u, img.orig_of_id[u], 100 * visits[u] / tv, 100 * vlook[u] / tl, vlook[u] / std::max(1.0, visits[u]), u >= h.gbase ? "branch" : "single");
+            if (u >= h.gbase) for (uint32_t q = 0; q < (1u << h.bucket_bits); q++) {
+                uint32_t e = tab[u + q], a = e & 0xFF, b = (e >> 8) & 0xFF;
+                if (a <= b) printf(" [%02x %02x]", a, b); else if (a == 0xFF && b == CODE_INDIRECT) { int n = 1; for (uint32_t x = (e >> 16) & 0x7FFF; tab[x] & TAB_MORE; x++) n++; printf(" I%d", n); } else if (a == 0xFF) printf(" -"); else printf(" C");
+            }
+            printf("\n");
+        }
+    }
+    // lock-step warp bound: mean over (warp, symbol) of max over its 32 lanes
+    double sum_max = 0, sum_tot = 0, sum_maxe = 0; uint64_t cnt = 0;
+    for (int w0 = 0; w0 + 32 <= n_streams; w0 += 32)
+        for (uint32_t k = 0; k < L; k++) {
+            uint32_t m = 0, tot = 0, me = 0;
+            for (int l = 0; l < 32; l++) { m = std::max(m, per_sym_lookups[w0 + l][k]); tot += per_sym_lookups[w0 + l][k]; me = std::max(me, per_sym_entries[w0 + l][k]); }
+            sum_max += m; sum_tot += tot; sum_maxe += me; cnt++;
+        }
+    printf("per warp-symbol: max-lane lookups %.2f  max-lane entries %.2f  total lookups %.2f (=> %.2f balanced iterations)\n", sum_max / cnt, sum_maxe / cnt, sum_tot / cnt, sum_tot / cnt / 32);
+    return 0;
+}
