@@ -44,18 +44,21 @@ struct ImageOptions {
     uint32_t max_bytes = 200 * 1024;
 };
 
-struct ImageHeader {  // mirrored on the device (kernels.cuh)
+struct ImageHeader {  // mirrored on the device (passed by value to the kernels)
     uint32_t n_slots;       // entries in tab
-    uint32_t gbase;         // first slot of the branching-state rows
+    uint32_t gbase;         // first slot of the hashed rows (branching states, then sticky rows)
     uint32_t nsb;           // sticky bits = 64 * sticky_words; ids < nsb are mask-resident
     uint32_t sticky_words;
     uint32_t bucket_bits;
-    uint32_t hash_mul;      // bucket(c) = ((c * hash_mul) >> hash_shift) & (nb - 1)
+    uint32_t hash_mul;      // h(c) = ((c * hash_mul) >> hash_shift) & 0xFF; bucket = h(c) & row mask
     uint32_t hash_shift;
     uint32_t start_id;      // internal id of state 0
     uint32_t n_sets;
+    uint32_t acc_base;      // accepting states own the contiguous id range [acc_base, acc_base + n_acc)
+    uint32_t n_acc;
+    uint32_t srow_base;     // first slot of the sticky rows (sized per state, see off_sdesc)
     // byte offsets of the sections inside the blob (all 16-byte aligned)
-    uint32_t off_tab, off_inj, off_mask, off_memb, off_tlist;
+    uint32_t off_tab, off_mask, off_memb, off_sdesc;   // sdesc[b] = row base | (row mask << 16) of sticky bit b
     uint32_t blob_bytes;
 };
 
@@ -63,7 +66,7 @@ struct Image {
     bool ok = false;
     std::string why_not;               // reason when !ok
     ImageHeader h{};
-    std::vector<uint8_t> blob;         // tab | inj | mask | memb | tlist, staged verbatim into smem
+    std::vector<uint8_t> blob;         // tab | mask | memb, staged verbatim into shared memory
     std::vector<uint32_t> orig_of_id;  // internal id -> original state id (0xFFFFFFFF: not a state)
     std::vector<uint32_t> id_of_orig;  // original state id -> internal id
     uint32_t n_sticky = 0;
@@ -75,7 +78,7 @@ inline uint32_t tab_pack(uint32_t a, uint32_t b, uint32_t tgt, bool more) {
     return (a & 0xFF) | ((b & 0xFF) << 8) | ((tgt & 0x7FFF) << 16) | (more ? TAB_MORE : 0u);
 }
 // a > b encodes a special: code = (0xFF - a) * 256 + b
-constexpr uint32_t CODE_EMPTY = 0, CODE_ACCEPT = 1, CODE_INDIRECT = 2, CODE_CLASS0 = 256;
+constexpr uint32_t CODE_INDIRECT = 2;
 inline uint32_t tab_special(uint32_t code, uint32_t tgt, bool more) {
     return tab_pack(0xFF - (code >> 8), code & 0xFF, tgt, more);
 }

@@ -6,17 +6,23 @@
 // (SURVEY.md 3.2).  The image removes both without changing what is computed:
 //
 //   * "sticky" states (self-loop on >= sticky_min_self symbols) live in a per-stream bit mask P.
-//     Per symbol c:  P' = (P & K[c]) | newly-entered;  injections = targets of (P & M[c]).
-//     K[c] bit b = sticky state b self-loops on c;  M[c] bit b = it has a non-self edge on c;
-//     A[c] = ~K[c] | M[c] lets the kernel skip both when nothing happens.
-//   * every other state is an id into one table of 32-bit edge records `tab`:
-//       - a state with a single (symbol-set -> target) edge or no edge is ONE record;
-//       - a branching state is a row of 2^bucket_bits records indexed by a hash of the symbol;
-//         a bucket holding several edges redirects to a contiguous chain.
+//     Per symbol c:  P' = (P & K[c]) | newly-entered;  the states in P & M[c] additionally fire their
+//     non-self edges.  K[c] bit b = sticky state b self-loops on c;  M[c] bit b = it has a non-self
+//     edge on c;  A[c] = ~K[c] | M[c] lets the kernel skip both when nothing happens.
+//   * every state's (non-self, for sticky states) edges live in ONE table of 32-bit records `tab`:
+//       - a state with a single (symbol-set -> target) edge is ONE record at tab[id];
+//       - a branching state, and every sticky state, is a row of 2^bucket_bits records indexed by a
+//         hash h(c) of the symbol: a branching state's row has 2^bucket_bits records at
+//         tab[id + (h(c) & (2^bucket_bits - 1))]; the row of sticky bit b is sized to that state
+//         (1..256 records, sdesc[b] = base | mask << 16) so that its firing costs one lookup;
+//         a bucket holding several edges redirects to a contiguous chain; an empty bucket holds a
+//         pair that cannot match in that bucket.
 //     record = a[7:0] | b[15:8] | target_id[30:16] | more[31]
-//       a <= b : edge taken iff c == a or c == b
-//       a == 0xFF > b : b = 0 empty, 1 accepting state, 2 indirect (target_id = chain start)
-//       a in {0xFE,0xFD} > b : edge taken iff c is in class set (0xFE - a) * 253 + b
+//       a <= b            : edge taken iff c == a or c == b
+//       a == 0xFF > b     : indirect, target_id = index of the chain
+//       a in {0xFE,0xFD}  : edge taken iff c is in class set (0xFE - a) * 253 + b   (b < 253)
+//   * accepting (zero-out-degree) states own the contiguous id range [acc_base, acc_base + n_acc):
+//     the kernel reports them when it pops them, without a table lookup.
 //   * state ids are internal (sticky ids < 64 * sticky_words); orig_of_id restores the reference's
 //     state numbers in every match record.
 //
@@ -48,9 +54,7 @@ struct Edge { uint32_t tgt; SymSet syms; };  // tgt = ORIGINAL state id
 
 inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
 
-}  // namespace
-
-static int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::string &err) {
+int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::string &err) {
     img = Image();
     const uint32_t N = nfa.n_states;
     const uint32_t *rp = nfa.row_ptr();
@@ -80,6 +84,12 @@ static int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, 
     std::vector<int32_t> sticky_bit(N, -1);
     for (size_t b = 0; b < cand.size(); b++) sticky_bit[cand[b]] = (int32_t)b;
     img.n_sticky = (uint32_t)cand.size();
+    // a sticky state keeps its self loop in K; only its other edges go to its row
+    for (uint32_t p : cand) {
+        std::vector<Edge> keep;
+        for (const Edge &e : edges[p]) if (e.tgt != p) keep.push_back(e);
+        edges[p].swap(keep);
+    }
 
     // ---- class sets (more than two symbols) ------------------------------------------------------
     std::map<SymSet, uint32_t> set_id;
@@ -91,39 +101,43 @@ static int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, 
         return id;
     };
 
-    // ---- id assignment ---------------------------------------------------------------------------
-    // non-sticky edges of a non-sticky state (the self loop is an ordinary edge there)
-    auto is_single = [&](uint32_t s) { return edges[s].size() <= 1; };
+    // ---- id assignment: [0,nsb) sticky | accepting | single-edge | hashed rows | sticky rows | chains ----
+    auto is_accept = [&](uint32_t s) { return rp[s] == rp[s + 1]; };
+    auto is_single = [&](uint32_t s) { return edges[s].size() == 1; };
     img.id_of_orig.assign(N, 0xFFFFFFFFu);
-    uint32_t next_id = nsb;
     for (size_t b = 0; b < cand.size(); b++) img.id_of_orig[cand[b]] = (uint32_t)b;
-    for (uint32_t s = 0; s < N; s++)
-        if (sticky_bit[s] < 0 && is_single(s)) img.id_of_orig[s] = next_id++;
+    uint32_t next_id = nsb;
+    const uint32_t acc_base = next_id;
+    for (uint32_t s = 0; s < N; s++) if (sticky_bit[s] < 0 && is_accept(s)) img.id_of_orig[s] = next_id++;
+    const uint32_t n_acc = next_id - acc_base;
+    for (uint32_t s = 0; s < N; s++) if (sticky_bit[s] < 0 && !is_accept(s) && is_single(s)) img.id_of_orig[s] = next_id++;
     const uint32_t gbase = next_id;
     int bb = opt.bucket_bits;
-    uint32_t n_branch = 0;
-    for (uint32_t s = 0; s < N; s++) n_branch += (sticky_bit[s] < 0 && !is_single(s));
-    if (bb < 0) bb = 4;
+    if (bb < 1) bb = 4;
     if (bb > 6) bb = 6;
     const uint32_t NB = 1u << bb;
+    std::vector<uint32_t> branchers;
     for (uint32_t s = 0; s < N; s++)
-        if (sticky_bit[s] < 0 && !is_single(s)) { img.id_of_orig[s] = next_id; next_id += NB; }
-    const uint32_t chain_base = next_id;
+        if (sticky_bit[s] < 0 && !is_accept(s) && !is_single(s)) { img.id_of_orig[s] = next_id; next_id += NB; branchers.push_back(s); }
+    const uint32_t srow_base = next_id;   // sticky rows are sized once the hash is known
 
     // ---- bucket hash: pick (mul, shift) minimising the expected table lookups per visit -------------
     // A visit with symbol c costs 1 lookup when bucket(c) holds <= 1 edge, 1 + n when it holds n >= 2
     // (indirection + chain).  Symbols that appear on some edge of the state are what the traffic that
-    // activated the state tends to continue with, so they carry the weight; all others share weight 1.
-    auto bucket_of = [&](uint32_t c, uint32_t mul, uint32_t sh) { return ((c * mul) >> sh) & (NB - 1); };
+    // activated the state tends to continue with, so they carry half the weight; all others the rest.
+    auto hfull = [&](uint32_t c, uint32_t mul, uint32_t sh) { return ((c * mul) >> sh) & 0xFFu; };
+    auto bucket_of = [&](uint32_t c, uint32_t mul, uint32_t sh) { return hfull(c, mul, sh) & (NB - 1); };
     uint32_t best_mul = 1, best_sh = 0;
     double best_cost = 1e300;
-    std::vector<uint32_t> branchers;
-    for (uint32_t s = 0; s < N; s++) if (sticky_bit[s] < 0 && !is_single(s)) branchers.push_back(s);
     for (uint32_t mul = 1; mul < 64; mul += 2)
         for (uint32_t sh = 0; sh < 8; sh++) {
+            bool seen8[256] = {false}, bij = true;      // h must be a bijection so that 256-slot rows are direct
+            for (uint32_t c = 0; c < 256 && bij; c++) { uint32_t v = hfull(c, mul, sh); bij = !seen8[v]; seen8[v] = true; }
+            if (!bij) continue;
             double cost = 0;
             for (uint32_t s : branchers) {
                 if (cost >= best_cost) break;
+                if (edges[s].empty()) continue;
                 uint32_t per_bucket[64] = {0};
                 SymSet used;
                 for (const Edge &e : edges[s]) {
@@ -141,9 +155,34 @@ static int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, 
             if (cost < best_cost) { best_cost = cost; best_mul = mul; best_sh = sh; }
         }
 
+    // ---- sticky rows: the smallest power-of-two row in which no two edges share a bucket (<= 256) ----
+    std::vector<uint32_t> srow_bits(nsb, 0), srow_off(nsb, 0);
+    {
+        uint32_t off = srow_base;
+        for (uint32_t b = 0; b < nsb; b++) {
+            uint32_t bits = 0;
+            if (b < cand.size()) {
+                for (; bits < 8; bits++) {
+                    bool clash = false;
+                    std::vector<int> owner(1u << bits, -1);
+                    for (size_t ei = 0; ei < edges[cand[b]].size() && !clash; ei++)
+                        for (uint32_t c : edges[cand[b]][ei].syms.members()) {
+                            int &o = owner[hfull(c, best_mul, best_sh) & ((1u << bits) - 1)];
+                            if (o >= 0 && o != (int)ei) { clash = true; break; }
+                            o = (int)ei;
+                        }
+                    if (!clash) break;
+                }
+            }
+            srow_bits[b] = bits; srow_off[b] = off; off += 1u << bits;
+        }
+        next_id = off;
+    }
+    const uint32_t chain_base = next_id;
+
     // ---- fill tab ----------------------------------------------------------------------------------
-    std::vector<uint32_t> tab(chain_base, tab_special(CODE_EMPTY, 0, false));
     bool ids_ok = true;
+    std::vector<uint32_t> tab(chain_base, tab_pack(0, 0, 0, false));
     auto record_for = [&](const Edge &e, const SymSet &visible, bool more) -> uint32_t {
         // `visible` = the symbols that can reach this record; inside it the edge must fire iff c in e.syms
         SymSet eff = e.syms & visible;
@@ -157,59 +196,56 @@ static int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, 
     };
     SymSet all;
     for (uint32_t c = 0; c < 256; c++) all.set(c);
-    for (uint32_t s = 0; s < N; s++) {
-        if (sticky_bit[s] >= 0) continue;
-        const uint32_t id = img.id_of_orig[s];
-        if (is_single(s)) {
-            if (edges[s].empty()) tab[id] = tab_special(CODE_ACCEPT, 0, false);  // Design/FPGA.v:210-213
-            else tab[id] = record_for(edges[s][0], all, false);
-            continue;
-        }
-        for (uint32_t q = 0; q < NB; q++) {
-            SymSet vis;
-            for (uint32_t c = 0; c < 256; c++) if (bucket_of(c, best_mul, best_sh) == q) vis.set(c);
+    auto fill_row = [&](uint32_t row, uint32_t bits, const std::vector<Edge> &ed) {
+        const uint32_t nb = 1u << bits;
+        for (uint32_t q = 0; q < nb; q++) {
+            SymSet vis;                       // symbols that reach bucket q of this row
+            int never = -1;                   // a symbol that cannot (filler for an empty bucket)
+            for (uint32_t c = 0; c < 256; c++) { if ((hfull(c, best_mul, best_sh) & (nb - 1)) == q) vis.set(c); else if (never < 0) never = (int)c; }
             std::vector<const Edge *> in;
-            for (const Edge &e : edges[s]) if ((e.syms & vis).any()) in.push_back(&e);
-            if (in.empty()) continue;  // stays EMPTY
-            if (in.size() == 1) { tab[id + q] = record_for(*in[0], vis, false); continue; }
+            for (const Edge &e : ed) if ((e.syms & vis).any()) in.push_back(&e);
+            if (in.empty()) {
+                if (never >= 0) tab[row + q] = tab_pack((uint32_t)never, (uint32_t)never, 0, false);
+                else { uint32_t n = class_of(SymSet()); tab[row + q] = tab_pack(0xFE - n / 253, n % 253, 0, false); }  // 1-slot row: empty class
+                continue;
+            }
+            if (in.size() == 1) { tab[row + q] = record_for(*in[0], vis, false); continue; }
             uint32_t start = (uint32_t)tab.size();
             if (start > 0x7FFF) ids_ok = false;
-            tab[id + q] = tab_special(CODE_INDIRECT, start, false);
+            tab[row + q] = tab_special(CODE_INDIRECT, start, false);
             for (size_t k = 0; k < in.size(); k++) tab.push_back(record_for(*in[k], vis, k + 1 < in.size()));
         }
+    };
+    for (uint32_t s = 0; s < N; s++) {
+        if (sticky_bit[s] >= 0) { fill_row(srow_off[sticky_bit[s]], srow_bits[sticky_bit[s]], edges[s]); continue; }
+        const uint32_t id = img.id_of_orig[s];
+        if (is_accept(s)) continue;                     // reported by id range, never looked up
+        if (is_single(s)) tab[id] = record_for(edges[s][0], all, false);
+        else fill_row(id, (uint32_t)bb, edges[s]);
+    }
+    for (uint32_t b = (uint32_t)cand.size(); b < nsb; b++) fill_row(srow_off[b], 0, {});
+    std::vector<uint32_t> sdesc(nsb);
+    for (uint32_t b = 0; b < nsb; b++) {
+        if (srow_off[b] > 0xFFFF) ids_ok = false;
+        sdesc[b] = srow_off[b] | (((1u << srow_bits[b]) - 1) << 16);
     }
 
-    // ---- sticky tables -------------------------------------------------------------------------------
-    const uint32_t mstride = 32u * (uint32_t)W;  // bytes per symbol: A[W] (pad to 16) K[W] M[W]
+    // ---- sticky masks ----------------------------------------------------------------------------------
+    const uint32_t mstride = 32u * (uint32_t)W;  // bytes per symbol: A[W] (padded to 16) | K[W] | M[W]
     std::vector<uint8_t> mask(256 * mstride, 0);
-    std::vector<uint16_t> inj((size_t)nsb * 256, 0xFFFF);
-    std::vector<uint16_t> tlist;
-    for (size_t b = 0; b < cand.size(); b++) {
-        const uint32_t p = cand[b];
+    for (size_t b = 0; b < nsb; b++) {
         for (uint32_t c = 0; c < 256; c++) {
-            std::vector<uint32_t> tg;
-            for (const Edge &e : edges[p]) if (e.tgt != p && e.syms.has(c)) tg.push_back(img.id_of_orig[e.tgt]);
             uint64_t *A = reinterpret_cast<uint64_t *>(&mask[c * mstride]);
             uint64_t *K = reinterpret_cast<uint64_t *>(&mask[c * mstride + 16]);
             uint64_t *M = K + W;
             const uint64_t bit = 1ull << (b & 63);
+            if (b >= cand.size()) { K[b >> 6] |= bit; continue; }   // absent slot: inert
+            const uint32_t p = cand[b];
+            bool fires = false;
+            for (const Edge &e : edges[p]) fires = fires || e.syms.has(c);
             if (selfset[p].has(c)) K[b >> 6] |= bit; else A[b >> 6] |= bit;
-            if (!tg.empty()) {
-                M[b >> 6] |= bit; A[b >> 6] |= bit;
-                for (uint32_t t : tg) if (t > 0x7FFF) ids_ok = false;
-                if (tg.size() == 1) inj[b * 256 + c] = (uint16_t)tg[0];
-                else {
-                    if (tlist.size() + tg.size() > 0x7FFE) ids_ok = false;
-                    inj[b * 256 + c] = (uint16_t)(0x8000u | tlist.size());
-                    for (size_t k = 0; k < tg.size(); k++) tlist.push_back((uint16_t)(tg[k] | (k + 1 < tg.size() ? 0x8000u : 0u)));
-                }
-            }
+            if (fires) { M[b >> 6] |= bit; A[b >> 6] |= bit; }
         }
-    }
-    // bits of absent sticky slots: K = 1 (harmless), A = 0
-    for (uint32_t c = 0; c < 256; c++) {
-        uint64_t *K = reinterpret_cast<uint64_t *>(&mask[c * mstride + 16]);
-        for (uint32_t b = (uint32_t)cand.size(); b < nsb; b++) K[b >> 6] |= 1ull << (b & 63);
     }
 
     // ---- class membership bitmaps ---------------------------------------------------------------------
@@ -220,7 +256,7 @@ static int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, 
 
     // ---- feasibility -------------------------------------------------------------------------------------
     if (tab.size() > 0x8000) ids_ok = false;
-    if (set_id.size() > 506) { img.why_not = "more than 506 distinct symbol classes"; }
+    if (set_id.size() > 506) img.why_not = "more than 506 distinct symbol classes";
     if (!ids_ok && img.why_not.empty()) img.why_not = "edge table exceeds the 15-bit id space (" + std::to_string(tab.size()) + " slots)";
 
     // ---- blob ------------------------------------------------------------------------------------------------
@@ -234,20 +270,21 @@ static int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, 
     h.hash_shift = best_sh;
     h.start_id = img.id_of_orig[0];
     h.n_sets = (uint32_t)set_id.size();
+    h.acc_base = acc_base;
+    h.n_acc = n_acc;
+    h.srow_base = srow_base;
     uint32_t off = 0;
     h.off_tab = off;   off = align16(off + (uint32_t)tab.size() * 4);
-    h.off_inj = off;   off = align16(off + (uint32_t)inj.size() * 2);
     h.off_mask = off;  off = align16(off + (uint32_t)mask.size());
     h.off_memb = off;  off = align16(off + (uint32_t)memb.size() * 4);
-    h.off_tlist = off; off = align16(off + (uint32_t)std::max<size_t>(8, tlist.size()) * 2);
+    h.off_sdesc = off; off = align16(off + (uint32_t)sdesc.size() * 4);
     h.blob_bytes = off;
     if (img.why_not.empty() && off > opt.max_bytes) img.why_not = "tables need " + std::to_string(off) + " bytes of shared memory (limit " + std::to_string(opt.max_bytes) + ")";
     img.blob.assign(off, 0);
     std::memcpy(&img.blob[h.off_tab], tab.data(), tab.size() * 4);
-    std::memcpy(&img.blob[h.off_inj], inj.data(), inj.size() * 2);
     std::memcpy(&img.blob[h.off_mask], mask.data(), mask.size());
     std::memcpy(&img.blob[h.off_memb], memb.data(), memb.size() * 4);
-    if (!tlist.empty()) std::memcpy(&img.blob[h.off_tlist], tlist.data(), tlist.size() * 2);
+    std::memcpy(&img.blob[h.off_sdesc], sdesc.data(), sdesc.size() * 4);
 
     img.orig_of_id.assign(tab.size(), 0xFFFFFFFFu);
     for (uint32_t s = 0; s < N; s++) if (img.id_of_orig[s] < img.orig_of_id.size()) img.orig_of_id[img.id_of_orig[s]] = s;
@@ -259,9 +296,11 @@ static int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, 
     return RFB_OK;
 }
 
-// bucket_bits < 0: the most buckets (up to 16 per branching state) whose tables still fit.
+}  // namespace
+
+// bucket_bits < 1: the most buckets (up to 16 per hashed row) whose tables still fit.
 int image_build(const Nfa &nfa, const ImageOptions &opt, Image &img, std::string &err) {
-    if (opt.bucket_bits >= 0) return image_build_one(nfa, opt, img, err);
+    if (opt.bucket_bits >= 1) return image_build_one(nfa, opt, img, err);
     ImageOptions o = opt;
     int rc = RFB_OK;
     for (int bb = 4; bb >= 1; bb--) {
@@ -272,47 +311,44 @@ int image_build(const Nfa &nfa, const ImageOptions &opt, Image &img, std::string
     return rc;
 }
 
-// The kernel's semantics, on the host.  Keep in lock-step with scan_lane.cu.
+// The kernel's semantics, on the host.  Keep in lock-step with scan_lane_kernel (scan.cu).
 void image_successors(const Image &img, uint32_t s, uint32_t c, std::vector<uint32_t> &out, bool *accepting) {
     const ImageHeader &h = img.h;
     const uint32_t *tab = reinterpret_cast<const uint32_t *>(&img.blob[h.off_tab]);
-    const uint16_t *inj = reinterpret_cast<const uint16_t *>(&img.blob[h.off_inj]);
     const uint32_t *memb = reinterpret_cast<const uint32_t *>(&img.blob[h.off_memb]);
-    const uint16_t *tlist = reinterpret_cast<const uint16_t *>(&img.blob[h.off_tlist]);
     const uint32_t mstride = 32u * h.sticky_words;
+    const uint32_t hf = ((c * h.hash_mul) >> h.hash_shift) & 0xFFu;
+    const uint32_t hc = hf & ((1u << h.bucket_bits) - 1);
+    const uint32_t *sdesc = reinterpret_cast<const uint32_t *>(&img.blob[h.off_sdesc]);
     out.clear();
     if (accepting) *accepting = false;
     const uint32_t id = img.id_of_orig[s];
     std::vector<uint32_t> ids;
+    uint32_t idx = 0;
+    bool walk = false;
     if (id < h.nsb) {
         const uint64_t *K = reinterpret_cast<const uint64_t *>(&img.blob[h.off_mask + c * mstride + 16]);
         const uint64_t *M = K + h.sticky_words;
         const uint64_t bit = 1ull << (id & 63);
         if (K[id >> 6] & bit) ids.push_back(id);
-        if (M[id >> 6] & bit) {
-            uint32_t x = inj[id * 256 + c];
-            if (x != 0xFFFF) {
-                if (x < 0x8000) ids.push_back(x);
-                else for (uint32_t q = x & 0x7FFF;; q++) { ids.push_back(tlist[q] & 0x7FFF); if (!(tlist[q] & 0x8000)) break; }
-            }
-        }
+        if (M[id >> 6] & bit) { idx = (sdesc[id] & 0xFFFFu) + (hf & (sdesc[id] >> 16)); walk = true; }
+    } else if (id - h.acc_base < h.n_acc) {
+        if (accepting) *accepting = true;
     } else {
-        uint32_t idx = id;
-        if (id >= h.gbase) idx += ((c * h.hash_mul) >> h.hash_shift) & ((1u << h.bucket_bits) - 1);
-        for (;;) {
-            const uint32_t e = tab[idx];
-            const uint32_t a = e & 0xFF, b = (e >> 8) & 0xFF, t = (e >> 16) & 0x7FFF;
-            if (a <= b) { if (c == a || c == b) ids.push_back(t); }
-            else if (a == 0xFF) {
-                if (b == CODE_ACCEPT) { if (accepting) *accepting = true; }
-                else if (b == CODE_INDIRECT) { idx = t; continue; }
-            } else {
-                const uint32_t n = (0xFE - a) * 253 + b;
-                if ((memb[n * 8 + (c >> 5)] >> (c & 31)) & 1) ids.push_back(t);
-            }
-            if (!(e & TAB_MORE)) break;
-            idx++;
+        idx = id + (id >= h.gbase ? hc : 0u);
+        walk = true;
+    }
+    while (walk) {
+        const uint32_t e = tab[idx];
+        const uint32_t a = e & 0xFF, b = (e >> 8) & 0xFF, t = (e >> 16) & 0x7FFF;
+        if (a <= b) { if (c == a || c == b) ids.push_back(t); }
+        else if (a == 0xFF) { idx = t; continue; }
+        else {
+            const uint32_t n = (0xFE - a) * 253 + b;
+            if ((memb[n * 8 + (c >> 5)] >> (c & 31)) & 1) ids.push_back(t);
         }
+        if (!(e & TAB_MORE)) break;
+        idx++;
     }
     for (uint32_t i : ids) out.push_back(i < img.orig_of_id.size() ? img.orig_of_id[i] : 0xFFFFFFFFu);
     std::sort(out.begin(), out.end());

@@ -76,18 +76,21 @@ __global__ void __launch_bounds__(LANE_THREADS, 1)
 scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     extern __shared__ __align__(128) uint8_t smem[];
     const ImageHeader &h = nfa.h;
-    uint16_t *lists = reinterpret_cast<uint16_t *>(smem + h.blob_bytes);
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + h.blob_bytes + (size_t)LANE_CAP * LANE_THREADS * sizeof(uint16_t));
+    constexpr uint32_t ROW = LANE_THREADS * 2;          // bytes between consecutive ring entries of one lane
+    constexpr uint32_t RING = LANE_CAP * ROW;           // bytes of the whole ring area
+    constexpr uint32_t RMASK = RING - 1;
+    uint8_t *lists = smem + h.blob_bytes;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + h.blob_bytes + RING);
     stage_image(smem, nfa.blob, h.blob_bytes, bar);
 
     const uint32_t *tab = reinterpret_cast<const uint32_t *>(smem + h.off_tab);
-    const uint16_t *inj = reinterpret_cast<const uint16_t *>(smem + h.off_inj);
     const uint8_t *mask = smem + h.off_mask;
     const uint32_t *memb = reinterpret_cast<const uint32_t *>(smem + h.off_memb);
-    const uint16_t *tlist = reinterpret_cast<const uint16_t *>(smem + h.off_tlist);
-    uint16_t *list = lists + threadIdx.x;  // entry i of this lane: list[i * LANE_THREADS]
+    const uint32_t *sdesc = reinterpret_cast<const uint32_t *>(smem + h.off_sdesc);
+    uint8_t *lb = lists + threadIdx.x * 2;              // ring entry at byte offset o: *(uint16_t*)(lb + o)
     const uint32_t gbase = h.gbase, nsb = h.nsb, hmul = h.hash_mul, hsh = h.hash_shift;
     const uint32_t nbm = (1u << h.bucket_bits) - 1u;
+    const uint32_t acc_base = h.acc_base, n_acc = h.n_acc;
     constexpr uint32_t MSTRIDE = 32u * W;
     constexpr uint32_t FULL = 0xffffffffu;
     const uint32_t lane = threadIdx.x & 31u;
@@ -105,16 +108,15 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
         const uint32_t maxsteps = __reduce_max_sync(FULL, nsteps);
 
         // ---- per-lane stream state ----
-        uint64_t P[W], Pn[W];
-#pragma unroll
-        for (int w = 0; w < W; w++) { P[w] = 0; Pn[w] = 0; }
-        uint32_t head = 0, rd = 0, ncur = 0, nnew = 0, flo = 0, fhi = 0;
+        uint64_t P0 = 0, P1 = 0, Pn0 = 0, Pn1 = 0;      // sticky sets (P1/Pn1 unused when W == 1)
+        uint32_t rp = 0, re = 0, wp = 0;                // ring byte offsets: next read, end of current set, next write
+        uint32_t flo = 0, fhi = 0;                      // 64-bit membership filter of this step's new entries
         bool ovf = false;
         uint32_t ovf_at = 0;
         if (nsteps) {
             if (h.start_id < nsb) {                                                   // Design/FPGA.v:146-147
-                if (W == 1 || h.start_id < 64) P[0] |= 1ull << (h.start_id & 63); else P[W - 1] |= 1ull << (h.start_id & 63);
-            } else { list[0] = (uint16_t)h.start_id; ncur = 1; }
+                if (W == 1 || h.start_id < 64) P0 = 1ull << (h.start_id & 63); else P1 = 1ull << (h.start_id & 63);
+            } else { *reinterpret_cast<uint16_t *>(lb) = (uint16_t)h.start_id; re = ROW; wp = ROW; }
         }
         // input: aligned 16-byte chunks kept in registers, the first one shifted to the stream's first byte
         uint64_t blo = 0, bhi = 0, plo = 0, phi = 0;
@@ -141,28 +143,6 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             nextp += 16;
         }
 
-        auto push = [&](uint32_t t) {
-            if (t < nsb) {
-                const uint64_t bit = 1ull << (t & 63);
-                if (W == 1 || t < 64) Pn[0] |= bit; else Pn[W - 1] |= bit;
-                return;
-            }
-            const uint32_t bit = 1u << (t & 31);
-            const bool hi = (t & 32) != 0;
-            const uint32_t f = hi ? fhi : flo;
-            bool dup = false;
-            if (f & bit) {  // possible duplicate: exact check against this step's new entries
-                for (uint32_t j = 0; j < nnew; j++)
-                    if (list[((head + ncur + j) & (LANE_CAP - 1)) * LANE_THREADS] == t) { dup = true; break; }
-            }
-            if (!dup) {
-                if (ncur - rd + nnew >= (uint32_t)LANE_CAP) { ovf = true; return; }
-                list[((head + ncur + nnew) & (LANE_CAP - 1)) * LANE_THREADS] = (uint16_t)t;
-                nnew++;
-                if (hi) fhi |= bit; else flo |= bit;
-            }
-        };
-
         for (uint32_t k = 0; k < maxsteps; k++) {
             const bool act = k < nsteps && !ovf;
             // ---- next symbol ----
@@ -179,68 +159,100 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             blo = (blo >> 8) | (bhi << 56);
             bhi >>= 8;
             bufn--;
-            const uint32_t hc = ((c * hmul) >> hsh) & nbm;
+            const uint32_t hf = ((c * hmul) >> hsh) & 0xFFu;   // symbol hash; a row uses its low bits
+            const uint32_t hc = hf & nbm;
 
-            // ---- transient states of S_k: one table lookup per lane per iteration ----
-            bool walking = false;
-            uint32_t idx = 0;
-            bool work = act && rd < ncur;
-            while (__any_sync(FULL, work)) {
-                if (work) {
-                    if (!walking) {
-                        const uint32_t u = list[((head + rd) & (LANE_CAP - 1)) * LANE_THREADS];
-                        rd++;
-                        idx = u + (u >= gbase ? hc : 0u);
-                    }
-                    const uint32_t e = tab[idx];
-                    const uint32_t a = e & 0xFFu, b = (e >> 8) & 0xFFu, t = (e >> 16) & 0x7FFFu;
-                    bool hit = false, redirect = false;
-                    if (a <= b) hit = (c == a) | (c == b);
-                    else if (a == 0xFFu) {
-                        if (b == CODE_ACCEPT) emit_match(out, sid + batch.stream_id_base, k, nfa.orig_of_id[idx]);
-                        else if (b == CODE_INDIRECT) redirect = true;
+            // ---- sticky states: survivors P & K[c]; those in P & M[c] fire their rows below ----
+            uint64_t im0 = 0, im1 = 0;
+            if (act) {
+                const uint8_t *mrow = mask + c * MSTRIDE;
+                bool attn;
+                if (W == 1) attn = (P0 & *reinterpret_cast<const uint64_t *>(mrow)) != 0;
+                else {
+                    const uint4 a = *reinterpret_cast<const uint4 *>(mrow);
+                    attn = (((uint32_t)P0 & a.x) | ((uint32_t)(P0 >> 32) & a.y) | ((uint32_t)P1 & a.z) | ((uint32_t)(P1 >> 32) & a.w)) != 0;
+                }
+                if (attn) {
+                    if (W == 1) {
+                        const uint4 km = *reinterpret_cast<const uint4 *>(mrow + 16);
+                        im0 = P0 & ((uint64_t)km.z | ((uint64_t)km.w << 32));
+                        P0 &= (uint64_t)km.x | ((uint64_t)km.y << 32);
                     } else {
-                        const uint32_t n = (0xFEu - a) * 253u + b;
-                        hit = (memb[n * 8 + (c >> 5)] >> (c & 31)) & 1u;
+                        const uint4 kk = *reinterpret_cast<const uint4 *>(mrow + 16);
+                        const uint4 mm = *reinterpret_cast<const uint4 *>(mrow + 32);
+                        im0 = P0 & ((uint64_t)mm.x | ((uint64_t)mm.y << 32));
+                        im1 = P1 & ((uint64_t)mm.z | ((uint64_t)mm.w << 32));
+                        P0 &= (uint64_t)kk.x | ((uint64_t)kk.y << 32);
+                        P1 &= (uint64_t)kk.z | ((uint64_t)kk.w << 32);
                     }
-                    if (hit && !ovf) push(t);
-                    if (redirect) { idx = t; walking = true; }
-                    else if (e & TAB_MORE) { idx++; walking = true; }
-                    else walking = false;
-                    work = walking || rd < ncur;
                 }
             }
 
-            // ---- sticky states: P' = (P & K[c]) | entered ; injections from P & M[c] ----
-            if (act) {
-                const uint8_t *mrow = mask + c * MSTRIDE;
-                bool attn = false;
-#pragma unroll
-                for (int w = 0; w < W; w++) attn |= (P[w] & reinterpret_cast<const uint64_t *>(mrow)[w]) != 0;
-                if (attn) {
-#pragma unroll
-                    for (int w = 0; w < W; w++) {
-                        const uint64_t K = reinterpret_cast<const uint64_t *>(mrow + 16)[w];
-                        const uint64_t M = reinterpret_cast<const uint64_t *>(mrow + 16)[W + w];
-                        uint64_t im = P[w] & M;
-                        P[w] &= K;
-                        while (im) {
-                            const uint32_t bpos = (uint32_t)__ffsll((long long)im) - 1u;
-                            im &= im - 1;
-                            const uint32_t x = inj[(w * 64 + bpos) * 256 + c];
-                            if (ovf) continue;
-                            if (x < 0x8000u) push(x);
-                            else if (x != 0xFFFFu) {
-                                uint32_t q = x & 0x7FFFu, tl;
-                                do { tl = tlist[q++]; push(tl & 0x7FFFu); } while ((tl & 0x8000u) && !ovf);
+            // ---- expand S_k: one edge-table lookup per lane per iteration -------------------------------
+            // work items of a lane: its transient states (ring) and the rows of its firing sticky states
+            bool walking = false;
+            uint32_t idx = 0;
+            bool work = act && (rp != re || (im0 | im1) != 0);
+            while (__any_sync(FULL, work)) {
+                if (work) {
+                    bool look = true;
+                    if (!walking) {
+                        if (rp != re) {
+                            const uint32_t u = *reinterpret_cast<const uint16_t *>(lb + rp);
+                            rp = (rp + ROW) & RMASK;
+                            if (u - acc_base < n_acc) {   // accepting state found in S_k (Design/FPGA.v:210-226)
+                                emit_match(out, sid + batch.stream_id_base, k, nfa.orig_of_id[u]);
+                                look = false;
+                            } else idx = u + (u >= gbase ? hc : 0u);
+                        } else {
+                            uint32_t bit;
+                            if (W == 1 || im0) { bit = (uint32_t)__ffsll((long long)im0) - 1u; im0 &= im0 - 1; }
+                            else { bit = 63u + (uint32_t)__ffsll((long long)im1); im1 &= im1 - 1; }
+                            const uint32_t d = sdesc[bit];
+                            idx = (d & 0xFFFFu) + (hf & (d >> 16));
+                        }
+                    }
+                    if (look) {
+                        const uint32_t e = tab[idx];
+                        const uint32_t a = e & 0xFFu, b = (e >> 8) & 0xFFu, t = (e >> 16) & 0x7FFFu;
+                        bool hit;
+                        walking = (e & TAB_MORE) != 0;
+                        idx++;
+                        if (a <= b) hit = (c == a) | (c == b);
+                        else if (a == 0xFFu) { hit = false; idx = t; walking = true; }      // indirect -> chain
+                        else hit = (memb[((0xFEu - a) * 253u + b) * 8 + (c >> 5)] >> (c & 31)) & 1u;
+                        if (hit && !ovf) {
+                            if (t < nsb) {                                               // entering a sticky state
+                                const uint64_t sb = 1ull << (t & 63);
+                                if (W == 1 || t < 64) Pn0 |= sb; else Pn1 |= sb;
+                            } else {
+                                const uint32_t fb = 1u << (t & 31);
+                                const bool fh = (t & 32) != 0;
+                                bool dup = false;
+                                if ((fh ? fhi : flo) & fb) {   // possible duplicate: exact check of this step's new entries
+                                    for (uint32_t o = re; o != wp; o = (o + ROW) & RMASK)
+                                        if (*reinterpret_cast<const uint16_t *>(lb + o) == t) { dup = true; break; }
+                                }
+                                if (!dup) {
+                                    const uint32_t nw = (wp + ROW) & RMASK;
+                                    if (nw == rp) ovf = true;                            // ring full: hand the stream over
+                                    else {
+                                        *reinterpret_cast<uint16_t *>(lb + wp) = (uint16_t)t;
+                                        wp = nw;
+                                        if (fh) fhi |= fb; else flo |= fb;
+                                    }
+                                }
                             }
                         }
                     }
+                    work = walking || rp != re || (im0 | im1) != 0;
                 }
-#pragma unroll
-                for (int w = 0; w < W; w++) { P[w] |= Pn[w]; Pn[w] = 0; }
-                // current <= next (Design/FPGA.v:733-737)
-                head += ncur; rd = 0; ncur = nnew; nnew = 0; flo = 0; fhi = 0;
+            }
+
+            if (act) {   // current <= next (Design/FPGA.v:733-737)
+                P0 |= Pn0; Pn0 = 0;
+                if (W == 2) { P1 |= Pn1; Pn1 = 0; }
+                re = wp; flo = 0; fhi = 0;
                 if (ovf) ovf_at = k + 1;   // S_k was fully examined; the general kernel reports from step k+1 on
             }
         }

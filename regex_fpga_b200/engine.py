@@ -218,6 +218,10 @@ class Nfa:
         r.counts = counts_ptr
         r.records = records_ptr
         r.record_capacity = record_capacity
+        # cuda_stream: None -> the context's own stream; a cudaStream_t handle otherwise.  Handle 0 is the legacy
+        # default stream (torch's default): pass cudaStreamLegacy (1) so that NULL keeps meaning "context stream".
+        if cuda_stream is not None and int(cuda_stream) == 0:
+            cuda_stream = 1
         _check(self._L.rfb_scan_device(self.ctx._h, self._h, C.byref(b), flags, cuda_stream, C.byref(r)), self.ctx._h)
         return r
 

@@ -215,7 +215,8 @@ def test_large_batch_properties(gpu_ctx, snort):
 
     def run(t, flags=0):
         c = torch.zeros(snort.n_states, dtype=torch.int64, device="cuda:0")
-        r = nfa.scan_device(t.data_ptr(), t.numel(), t.shape[0], 1500, 1536, c.data_ptr(), None, 0, flags=flags)
+        r = nfa.scan_device(t.data_ptr(), t.numel(), t.shape[0], 1500, 1536, c.data_ptr(), None, 0, flags=flags,
+                            cuda_stream=torch.cuda.current_stream().cuda_stream)   # order after torch's own work
         return c.cpu().numpy(), r.n_matches
 
     c_all, m_all = run(dev)

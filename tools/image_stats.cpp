@@ -31,13 +31,11 @@ int main(int argc, char **argv) {
     if (nfa_from_entries(E.data(), E.size(), -1, nfa, err) || image_build(nfa, opt, img, err) || !img.ok) { fprintf(stderr, "image: %s %s\n", err.c_str(), img.why_not.c_str()); return 1; }
     const ImageHeader &h = img.h;
     const uint32_t *tab = (const uint32_t *)&img.blob[h.off_tab];
-    const uint16_t *inj = (const uint16_t *)&img.blob[h.off_inj];
     const uint32_t *memb = (const uint32_t *)&img.blob[h.off_memb];
-    const uint16_t *tlist = (const uint16_t *)&img.blob[h.off_tlist];
+    const uint32_t *sdesc = (const uint32_t *)&img.blob[h.off_sdesc];
     const uint32_t W = h.sticky_words, ms = 32 * W, L = 1500;
-    printf("image: slots %u gbase %u nsb %u W %u bucket_bits %u bytes %u sets %u sticky %u\n", h.n_slots, h.gbase, h.nsb, W, h.bucket_bits, h.blob_bytes, h.n_sets, img.n_sticky);
+    printf("image: slots %u gbase %u nsb %u W %u bucket_bits %u bytes %u sets %u sticky %u hash mul %u sh %u\n", h.n_slots, h.gbase, h.nsb, W, h.bucket_bits, h.blob_bytes, h.n_sets, img.n_sticky, h.hash_mul, h.hash_shift);
     Stats st[2];
-    std::vector<double> visits(h.n_slots,0), vlook(h.n_slots,0);
     std::vector<std::vector<uint32_t>> per_sym_lookups(n_streams, std::vector<uint32_t>(L));
     std::vector<std::vector<uint32_t>> per_sym_entries(n_streams, std::vector<uint32_t>(L));
     for (int j = 0; j < n_streams; j++) {
@@ -48,43 +46,38 @@ int main(int argc, char **argv) {
         std::vector<uint32_t> cur, nxt;
         if (h.start_id < h.nsb) P[h.start_id >> 6] |= 1ull << (h.start_id & 63); else cur.push_back(h.start_id);
         for (uint32_t k = 0; k < L; k++) {
-            uint32_t c = src[off + k], hc = ((c * h.hash_mul) >> h.hash_shift) & ((1u << h.bucket_bits) - 1);
+            uint32_t c = src[off + k], hf = ((c * h.hash_mul) >> h.hash_shift) & 0xFF, hc = hf & ((1u << h.bucket_bits) - 1);
             uint64_t Pn[2] = {0, 0};
             std::set<uint32_t> seen;
-            uint32_t lk = 0;
+            uint32_t lk = 0;   // loop iterations of this lane in this step (pops of accept states count too)
             auto push = [&](uint32_t t) { s.pushes++; if (t < h.nsb) Pn[t >> 6] |= 1ull << (t & 63); else if (seen.insert(t).second) nxt.push_back(t); };
-            s.entries += cur.size(); per_sym_entries[j][k] = cur.size();
-            s.maxlist = std::max<double>(s.maxlist, cur.size());
-            for (uint32_t u : cur) {
-                uint32_t idx = u + (u >= h.gbase ? hc : 0); uint32_t lk0 = lk; visits[u]++;
+            auto walk = [&](uint32_t idx) {
                 for (;;) {
                     uint32_t e = tab[idx]; lk++;
                     uint32_t a = e & 0xFF, b = (e >> 8) & 0xFF, t = (e >> 16) & 0x7FFF;
                     if (a <= b) { if (c == a || c == b) push(t); }
-                    else if (a == 0xFF) { if (b == CODE_INDIRECT) { s.indirect++; idx = t; continue; } }
+                    else if (a == 0xFF) { s.indirect++; idx = t; continue; }
                     else { s.cls++; uint32_t n = (0xFE - a) * 253 + b; if ((memb[n * 8 + (c >> 5)] >> (c & 31)) & 1) push(t); }
                     if (!(e & TAB_MORE)) break;
                     idx++;
                 }
-                vlook[u] += lk - lk0;
-            }
-            s.lookups += lk; per_sym_lookups[j][k] = lk;
+            };
+            s.entries += cur.size(); per_sym_entries[j][k] = cur.size();
+            s.maxlist = std::max<double>(s.maxlist, cur.size());
             const uint64_t *A = (const uint64_t *)&img.blob[h.off_mask + c * ms];
             const uint64_t *K = (const uint64_t *)&img.blob[h.off_mask + c * ms + 16];
             const uint64_t *M = K + W;
             bool attn = false;
+            uint64_t im[2] = {0, 0};
             for (uint32_t w = 0; w < W; w++) { attn |= (P[w] & A[w]) != 0; s.sticky += __builtin_popcountll(P[w]); }
-            if (attn) {
-                s.attn++;
-                for (uint32_t w = 0; w < W; w++) {
-                    uint64_t im = P[w] & M[w]; P[w] &= K[w];
-                    while (im) {
-                        uint32_t b = __builtin_ctzll(im); im &= im - 1; s.inj++;
-                        uint32_t x = inj[(w * 64 + b) * 256 + c];
-                        if (x < 0x8000) push(x); else if (x != 0xFFFF) for (uint32_t q = x & 0x7FFF;; q++) { push(tlist[q] & 0x7FFF); if (!(tlist[q] & 0x8000)) break; }
-                    }
-                }
+            if (attn) { s.attn++; for (uint32_t w = 0; w < W; w++) { im[w] = P[w] & M[w]; P[w] &= K[w]; } }
+            for (uint32_t u : cur) {
+                if (u - h.acc_base < h.n_acc) { lk++; continue; }
+                walk(u + (u >= h.gbase ? hc : 0));
             }
+            for (uint32_t w = 0; w < W; w++)
+                while (im[w]) { uint32_t b = __builtin_ctzll(im[w]) + 64 * w; im[w] &= im[w] - 1; s.inj++; walk((sdesc[b] & 0xFFFF) + (hf & (sdesc[b] >> 16))); }
+            s.lookups += lk; per_sym_lookups[j][k] = lk;
             for (uint32_t w = 0; w < W; w++) P[w] |= Pn[w];
             cur.swap(nxt); nxt.clear(); s.symbols++;
         }
@@ -93,20 +86,6 @@ int main(int argc, char **argv) {
         Stats &s = st[t];
         printf("%s: per symbol: entries %.3f lookups %.3f indirect %.3f class %.3f pushes %.3f attn %.3f inj %.3f sticky %.2f maxlist %.0f\n", t ? "hi" : "lo",
                s.entries / s.symbols, s.lookups / s.symbols, s.indirect / s.symbols, s.cls / s.symbols, s.pushes / s.symbols, s.attn / s.symbols, s.inj / s.symbols, s.sticky / s.symbols, s.maxlist);
-    }
-    {
-        std::vector<uint32_t> order(h.n_slots); for (uint32_t i = 0; i < h.n_slots; i++) order[i] = i;
-        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return vlook[a] > vlook[b]; });
-        double tv = 0, tl = 0; for (uint32_t i = 0; i < h.n_slots; i++) { tv += visits[i]; tl += vlook[i]; }
-        for (int r = 0; r < 14; r++) {
-            uint32_t u = order[r];
-            printf("  id %5u orig %5u visits %5.2f%% lookups %5.2f%% (%.2f/visit) %s row:", u, img.orig_of_id[u], 100 * visits[u] / tv, 100 * vlook[u] / tl, vlook[u] / std::max(1.0, visits[u]), u >= h.gbase ? "branch" : "single");
-            if (u >= h.gbase) for (uint32_t q = 0; q < (1u << h.bucket_bits); q++) {
-                uint32_t e = tab[u + q], a = e & 0xFF, b = (e >> 8) & 0xFF;
-                if (a <= b) printf(" [%02x %02x]", a, b); else if (a == 0xFF && b == CODE_INDIRECT) { int n = 1; for (uint32_t x = (e >> 16) & 0x7FFF; tab[x] & TAB_MORE; x++) n++; printf(" I%d", n); } else if (a == 0xFF) printf(" -"); else printf(" C");
-            }
-            printf("\n");
-        }
     }
     // lock-step warp bound: mean over (warp, symbol) of max over its 32 lanes
     double sum_max = 0, sum_tot = 0, sum_maxe = 0; uint64_t cnt = 0;
