@@ -89,7 +89,8 @@ static ImageOptions default_image_options() {
     if (const char *s = std::getenv("RFB_STICKY_WORDS")) opt.sticky_words = std::atoi(s);
     if (const char *s = std::getenv("RFB_BUCKET_BITS")) opt.bucket_bits = std::atoi(s);
     if (const char *s = std::getenv("RFB_STICKY_MIN_SELF")) opt.sticky_min_self = std::atoi(s);
-    opt.max_bytes = (uint32_t)(MAX_DYN_SMEM - (size_t)LANE_CAP * LANE_THREADS * sizeof(uint16_t) - 64);
+    // leave room for two 64-item lists and the filter of every warp beside the tables
+    opt.max_bytes = (uint32_t)(MAX_DYN_SMEM - (LANE_THREADS / 32) * (2 * 64 * 4 + 32 * 4) - 64);
     return opt;
 }
 

@@ -41,6 +41,7 @@ struct ImageOptions {
     int sticky_words = 0;       // 0 = auto (1 or 2)
     int sticky_min_self = 16;   // a state is mask-resident if it self-loops on >= this many symbols
     int bucket_bits = -1;       // -1 = auto; buckets per branching state = 1 << bucket_bits
+    int accel = 1;              // build the two-symbol start table for the busiest sticky state
     uint32_t max_bytes = 200 * 1024;
 };
 
@@ -59,6 +60,8 @@ struct ImageHeader {  // mirrored on the device (passed by value to the kernels)
     uint32_t srow_base;     // first slot of the sticky rows (sized per state, see off_sdesc)
     // byte offsets of the sections inside the blob (all 16-byte aligned)
     uint32_t off_tab, off_mask, off_memb, off_sdesc;   // sdesc[b] = row base | (row mask << 16) of sticky bit b
+    // two-symbol start table of the accelerated sticky state (bit 0); accel == 0: absent
+    uint32_t accel, nc2, off_cmap, off_t2, off_tl2;
     uint32_t blob_bytes;
 };
 
@@ -70,6 +73,9 @@ struct Image {
     std::vector<uint32_t> orig_of_id;  // internal id -> original state id (0xFFFFFFFF: not a state)
     std::vector<uint32_t> id_of_orig;  // original state id -> internal id
     uint32_t n_sticky = 0;
+    // accelerated sticky state (host-side description for the verifier)
+    uint32_t accel_state = 0xFFFFFFFFu;                 // original id
+    std::vector<std::vector<uint32_t>> virt_of_cls1;   // class of c1 -> virtual targets (original ids)
 };
 
 // tab entry encoding

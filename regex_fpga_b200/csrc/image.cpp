@@ -21,6 +21,12 @@
 //       a <= b            : edge taken iff c == a or c == b
 //       a == 0xFF > b     : indirect, target_id = index of the chain
 //       a in {0xFE,0xFD}  : edge taken iff c is in class set (0xFE - a) * 253 + b   (b < 253)
+//   * the busiest sticky state A (in an unanchored ruleset: the global ".*" state, active for ever)
+//     gets bit 0 and a two-symbol start table: its targets X that are neither sticky nor accepting are
+//     never materialised; instead T2[cls1(c_k)][cls2(c_k+1)] lists the successors of those X on the
+//     next symbol (the NFA step is a union over active states, so composing two steps of one always-
+//     firing state is exact).  cmap[c] = cls1 | cls2 << 8, T2 entries are 0xFFFF (none), a target id,
+//     or 0x8000 | offset of a target list.
 //   * accepting (zero-out-degree) states own the contiguous id range [acc_base, acc_base + n_acc):
 //     the kernel reports them when it pops them, without a table lookup.
 //   * state ids are internal (sticky ids < 64 * sticky_words); orig_of_id restores the reference's
@@ -91,6 +97,40 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
         edges[p].swap(keep);
     }
 
+    // ---- accelerated sticky state ---------------------------------------------------------------------
+    auto is_accept = [&](uint32_t s) { return rp[s] == rp[s + 1]; };
+    std::vector<Edge> virt_edges;    // A's edges to targets that are never materialised
+    std::vector<uint32_t> virt;      // those targets (original ids, sorted)
+    bool accel = false;
+    if (opt.accel && !cand.empty()) {
+        // Prefer a state that is active for ever in every stream (entered from state 0 on all 256 symbols
+        // and self-looping on all of them: the global ".*" of an unanchored ruleset); otherwise the state
+        // with the most never-materialisable targets.
+        SymSet all256;
+        for (uint32_t c = 0; c < 256; c++) all256.set(c);
+        size_t best = 0; int best_n = 0;
+        for (size_t b = 0; b < cand.size(); b++) {
+            int n = 0;
+            for (const Edge &e : edges[cand[b]]) n += (sticky_bit[e.tgt] < 0 && !is_accept(e.tgt));
+            if (n == 0) continue;
+            bool always = selfset[cand[b]] == all256;
+            if (always) { always = false; for (const Edge &e : edges[0]) if (e.tgt == cand[b] && e.syms == all256) always = true; }
+            if (always) n += 1000;
+            if (n > best_n) { best_n = n; best = b; }
+        }
+        if (best_n >= 4) {
+            std::swap(cand[0], cand[best]);
+            for (size_t b = 0; b < cand.size(); b++) sticky_bit[cand[b]] = (int32_t)b;
+            const uint32_t A = cand[0];
+            std::vector<Edge> keep;
+            for (const Edge &e : edges[A]) {
+                if (sticky_bit[e.tgt] < 0 && !is_accept(e.tgt)) { virt_edges.push_back(e); virt.push_back(e.tgt); }
+                else keep.push_back(e);
+            }
+            if (!virt_edges.empty()) { edges[A].swap(keep); accel = true; img.accel_state = A; }
+        }
+    }
+
     // ---- class sets (more than two symbols) ------------------------------------------------------
     std::map<SymSet, uint32_t> set_id;
     auto class_of = [&](const SymSet &s) -> uint32_t {
@@ -102,7 +142,6 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
     };
 
     // ---- id assignment: [0,nsb) sticky | accepting | single-edge | hashed rows | sticky rows | chains ----
-    auto is_accept = [&](uint32_t s) { return rp[s] == rp[s + 1]; };
     auto is_single = [&](uint32_t s) { return edges[s].size() == 1; };
     img.id_of_orig.assign(N, 0xFFFFFFFFu);
     for (size_t b = 0; b < cand.size(); b++) img.id_of_orig[cand[b]] = (uint32_t)b;
@@ -248,6 +287,49 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
         }
     }
 
+    // ---- two-symbol start table -------------------------------------------------------------------------
+    std::vector<uint16_t> cmap(256, 0), t2(1, 0xFFFF), tl2;
+    uint32_t nc1 = 1, nc2 = 1;
+    if (accel) {
+        std::map<std::vector<uint32_t>, uint32_t> c1id, c2id;
+        std::vector<uint32_t> rep2;                         // representative symbol of each cls2
+        c1id[{}] = 0; img.virt_of_cls1.push_back({});
+        std::vector<uint32_t> cls1(256), cls2(256);
+        auto succ = [&](uint32_t X, uint32_t c) { std::vector<uint32_t> v; for (const Edge &e : edges[X]) if (e.syms.has(c)) v.push_back(e.tgt); return v; };
+        for (uint32_t c = 0; c < 256; c++) {
+            std::vector<uint32_t> v;
+            for (const Edge &e : virt_edges) if (e.syms.has(c)) v.push_back(e.tgt);
+            std::sort(v.begin(), v.end());
+            auto it = c1id.find(v);
+            if (it == c1id.end()) { it = c1id.emplace(v, (uint32_t)c1id.size()).first; img.virt_of_cls1.push_back(v); }
+            cls1[c] = it->second;
+            std::vector<uint32_t> sig;                      // behaviour of c on every virtual target
+            for (uint32_t X : virt) { for (uint32_t t : succ(X, c)) sig.push_back(t); sig.push_back(0xFFFFFFFFu); }
+            auto jt = c2id.find(sig);
+            if (jt == c2id.end()) { jt = c2id.emplace(sig, (uint32_t)c2id.size()).first; rep2.push_back(c); }
+            cls2[c] = jt->second;
+        }
+        nc1 = (uint32_t)c1id.size(); nc2 = (uint32_t)c2id.size();
+        if (nc1 > 255 || nc2 > 255 || (size_t)nc1 * nc2 > 16384) { img.why_not = "two-symbol start table too large"; }
+        else {
+            t2.assign((size_t)nc1 * nc2, 0xFFFF);
+            for (uint32_t i = 0; i < nc1; i++)
+                for (uint32_t j = 0; j < nc2; j++) {
+                    std::vector<uint32_t> tg;
+                    for (uint32_t X : img.virt_of_cls1[i]) for (uint32_t t : succ(X, rep2[j])) tg.push_back(img.id_of_orig[t]);
+                    std::sort(tg.begin(), tg.end());
+                    tg.erase(std::unique(tg.begin(), tg.end()), tg.end());
+                    if (tg.empty()) continue;
+                    for (uint32_t t : tg) if (t > 0x7FFF) ids_ok = false;
+                    if (tg.size() == 1) { t2[i * nc2 + j] = (uint16_t)tg[0]; continue; }
+                    if (tl2.size() + tg.size() > 0x7FFE) { ids_ok = false; continue; }
+                    t2[i * nc2 + j] = (uint16_t)(0x8000u | tl2.size());
+                    for (size_t q = 0; q < tg.size(); q++) tl2.push_back((uint16_t)(tg[q] | (q + 1 < tg.size() ? 0x8000u : 0u)));
+                }
+            for (uint32_t c = 0; c < 256; c++) cmap[c] = (uint16_t)(cls1[c] | (cls2[c] << 8));
+        }
+    }
+
     // ---- class membership bitmaps ---------------------------------------------------------------------
     std::vector<uint32_t> memb(std::max<size_t>(1, set_id.size()) * 8, 0);
     for (auto &kv : set_id)
@@ -278,6 +360,11 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
     h.off_mask = off;  off = align16(off + (uint32_t)mask.size());
     h.off_memb = off;  off = align16(off + (uint32_t)memb.size() * 4);
     h.off_sdesc = off; off = align16(off + (uint32_t)sdesc.size() * 4);
+    h.accel = accel ? 1u : 0u;
+    h.nc2 = nc2;
+    h.off_cmap = off;  off = align16(off + 512);
+    h.off_t2 = off;    off = align16(off + (uint32_t)t2.size() * 2);
+    h.off_tl2 = off;   off = align16(off + (uint32_t)std::max<size_t>(8, tl2.size()) * 2);
     h.blob_bytes = off;
     if (img.why_not.empty() && off > opt.max_bytes) img.why_not = "tables need " + std::to_string(off) + " bytes of shared memory (limit " + std::to_string(opt.max_bytes) + ")";
     img.blob.assign(off, 0);
@@ -285,6 +372,9 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
     std::memcpy(&img.blob[h.off_mask], mask.data(), mask.size());
     std::memcpy(&img.blob[h.off_memb], memb.data(), memb.size() * 4);
     std::memcpy(&img.blob[h.off_sdesc], sdesc.data(), sdesc.size() * 4);
+    std::memcpy(&img.blob[h.off_cmap], cmap.data(), 512);
+    std::memcpy(&img.blob[h.off_t2], t2.data(), t2.size() * 2);
+    if (!tl2.empty()) std::memcpy(&img.blob[h.off_tl2], tl2.data(), tl2.size() * 2);
 
     img.orig_of_id.assign(tab.size(), 0xFFFFFFFFu);
     for (uint32_t s = 0; s < N; s++) if (img.id_of_orig[s] < img.orig_of_id.size()) img.orig_of_id[img.id_of_orig[s]] = s;
@@ -332,6 +422,10 @@ void image_successors(const Image &img, uint32_t s, uint32_t c, std::vector<uint
         const uint64_t bit = 1ull << (id & 63);
         if (K[id >> 6] & bit) ids.push_back(id);
         if (M[id >> 6] & bit) { idx = (sdesc[id] & 0xFFFFu) + (hf & (sdesc[id] >> 16)); walk = true; }
+        if (h.accel && id == 0) {   // targets reached only through the two-symbol table (checked in image_verify)
+            const uint16_t *cmap = reinterpret_cast<const uint16_t *>(&img.blob[h.off_cmap]);
+            for (uint32_t X : img.virt_of_cls1[cmap[c] & 0xFF]) ids.push_back(img.id_of_orig[X]);
+        }
     } else if (id - h.acc_base < h.n_acc) {
         if (accepting) *accepting = true;
     } else {
@@ -373,6 +467,32 @@ int image_verify(const Nfa &nfa, const Image &img, std::string &err) {
             if (got != want || acc != (rp[s] == rp[s + 1])) {
                 err = "execution image disagrees with the CSR at state " + std::to_string(s) + " symbol " + std::to_string(c);
                 return RFB_E_INTERNAL;
+            }
+        }
+    }
+    if (img.h.accel) {   // T2[cls1(c1)][cls2(c2)] == successors on c2 of the virtual targets of A on c1
+        const ImageHeader &h = img.h;
+        const uint16_t *cmap = reinterpret_cast<const uint16_t *>(&img.blob[h.off_cmap]);
+        const uint16_t *t2 = reinterpret_cast<const uint16_t *>(&img.blob[h.off_t2]);
+        const uint16_t *tl2 = reinterpret_cast<const uint16_t *>(&img.blob[h.off_tl2]);
+        for (uint32_t c1 = 0; c1 < 256; c1++) {
+            const std::vector<uint32_t> &V = img.virt_of_cls1[cmap[c1] & 0xFF];
+            for (uint32_t X : V)
+                if (img.id_of_orig[X] < h.nsb || rp[X] == rp[X + 1]) { err = "two-symbol table hides a sticky or accepting state"; return RFB_E_INTERNAL; }
+            for (uint32_t c2 = 0; c2 < 256; c2++) {
+                want.clear();
+                for (uint32_t X : V)
+                    for (uint32_t j = rp[X]; j < rp[X + 1]; j++) if ((tr[j] >> 24) == c2) want.push_back(tr[j] & 0xFFFFFFu);
+                std::sort(want.begin(), want.end());
+                want.erase(std::unique(want.begin(), want.end()), want.end());
+                got.clear();
+                const uint32_t x = t2[(cmap[c1] & 0xFF) * h.nc2 + (cmap[c2] >> 8)];
+                if (x != 0xFFFF) {
+                    if (x < 0x8000) got.push_back(img.orig_of_id[x]);
+                    else for (uint32_t q = x & 0x7FFF;; q++) { got.push_back(img.orig_of_id[tl2[q] & 0x7FFF]); if (!(tl2[q] & 0x8000)) break; }
+                }
+                std::sort(got.begin(), got.end());
+                if (got != want) { err = "two-symbol start table disagrees with the CSR at symbols " + std::to_string(c1) + "," + std::to_string(c2); return RFB_E_INTERNAL; }
             }
         }
     }

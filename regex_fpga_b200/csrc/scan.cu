@@ -67,36 +67,63 @@ __device__ __forceinline__ void stage_image(uint8_t *dst, const uint8_t *src, ui
 // ------------------------------------------------------------------------------------------------
 // lane kernel
 // ------------------------------------------------------------------------------------------------
-size_t lane_smem_bytes(const ImageHeader &h) {
-    return (size_t)h.blob_bytes + (size_t)LANE_CAP * LANE_THREADS * sizeof(uint16_t) + 16;
+
+// out-of-line copy for the lane kernel's hot loop (matches are rare there)
+__device__ __noinline__ void emit_match_cold(const OutDev &out, uint32_t stream, uint32_t pos, uint32_t state) {
+    emit_match(out, stream, pos, state);
+}
+
+// Work items of the warp-shared list: owner lane in bits 16..20, 16-bit value in bits 0..15.
+//   kind STATE  : value = internal state id (a member of S_k; accept ids are reported, others looked up)
+//   kind ROW    : value = edge-table index already hashed (row of a firing sticky state)
+//   kind DIRECT : value = target id to add to S_{k+1} as is (two-symbol start table hit)
+constexpr uint32_t ITEM_ROW = 1u << 30, ITEM_DIRECT = 1u << 31;
+constexpr uint32_t LANE_FILT_WORDS = 32;   // 1024-bit membership filter per warp
+
+size_t lane_smem_bytes(const ImageHeader &h, uint32_t wcap) {
+    const size_t warps = LANE_THREADS / 32;
+    return (size_t)h.blob_bytes + warps * (2 * (size_t)wcap * 4 + LANE_FILT_WORDS * 4) + 16;
+}
+uint32_t lane_wcap_for(const ImageHeader &h) {
+    const size_t warps = LANE_THREADS / 32;
+    const size_t avail = MAX_DYN_SMEM - h.blob_bytes - warps * LANE_FILT_WORDS * 4 - 64;
+    size_t wcap = avail / (warps * 8);
+    wcap = wcap / 32 * 32;
+    return (uint32_t)(wcap > 512 ? 512 : wcap);
 }
 
 template <int W>
 __global__ void __launch_bounds__(LANE_THREADS, 1)
-scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
+scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const uint32_t wcap) {
     extern __shared__ __align__(128) uint8_t smem[];
     const ImageHeader &h = nfa.h;
-    constexpr uint32_t ROW = LANE_THREADS * 2;          // bytes between consecutive ring entries of one lane
-    constexpr uint32_t RING = LANE_CAP * ROW;           // bytes of the whole ring area
-    constexpr uint32_t RMASK = RING - 1;
-    uint8_t *lists = smem + h.blob_bytes;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + h.blob_bytes + RING);
+    constexpr uint32_t WARPS = LANE_THREADS / 32;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t ltmask = (1u << lane) - 1u;
+    uint32_t *wl_base = reinterpret_cast<uint32_t *>(smem + h.blob_bytes);
+    uint32_t *cur = wl_base + (size_t)warp * 2 * wcap;       // items of S_k (plus this step's own-stream items)
+    uint32_t *nxt = cur + wcap;                              // members of S_{k+1} being collected
+    uint32_t *filt = wl_base + (size_t)WARPS * 2 * wcap + warp * LANE_FILT_WORDS;
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + h.blob_bytes + (size_t)WARPS * (2 * (size_t)wcap * 4 + LANE_FILT_WORDS * 4));
     stage_image(smem, nfa.blob, h.blob_bytes, bar);
 
     const uint32_t *tab = reinterpret_cast<const uint32_t *>(smem + h.off_tab);
     const uint8_t *mask = smem + h.off_mask;
     const uint32_t *memb = reinterpret_cast<const uint32_t *>(smem + h.off_memb);
     const uint32_t *sdesc = reinterpret_cast<const uint32_t *>(smem + h.off_sdesc);
-    uint8_t *lb = lists + threadIdx.x * 2;              // ring entry at byte offset o: *(uint16_t*)(lb + o)
+    const uint16_t *cmap = reinterpret_cast<const uint16_t *>(smem + h.off_cmap);
+    const uint16_t *t2 = reinterpret_cast<const uint16_t *>(smem + h.off_t2);
+    const uint16_t *tl2 = reinterpret_cast<const uint16_t *>(smem + h.off_tl2);
     const uint32_t gbase = h.gbase, nsb = h.nsb, hmul = h.hash_mul, hsh = h.hash_shift;
     const uint32_t nbm = (1u << h.bucket_bits) - 1u;
-    const uint32_t acc_base = h.acc_base, n_acc = h.n_acc;
+    const uint32_t acc_base = h.acc_base, n_acc = h.n_acc, nc2 = h.nc2;
+    const bool accel = h.accel != 0;
     constexpr uint32_t MSTRIDE = 32u * W;
-    constexpr uint32_t FULL = 0xffffffffu;
-    const uint32_t lane = threadIdx.x & 31u;
 
-    // A warp takes 32 consecutive streams at a time and steps them in lock-step, one symbol per
-    // iteration of the k loop, so that the per-symbol bookkeeping runs with all 32 lanes converged.
+    // A warp takes 32 consecutive streams at a time (one per lane) and steps them in lock-step.  The
+    // transient members of all 32 current sets live in ONE warp-shared list, so that the edge-table
+    // lookups of a step are spread over all lanes no matter how unevenly the streams are loaded.
     for (;;) {
         unsigned int base = 0;
         if (lane == 0) base = atomicAdd(&out.g->next_stream, 32u);
@@ -109,14 +136,20 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
 
         // ---- per-lane stream state ----
         uint64_t P0 = 0, P1 = 0, Pn0 = 0, Pn1 = 0;      // sticky sets (P1/Pn1 unused when W == 1)
-        uint32_t rp = 0, re = 0, wp = 0;                // ring byte offsets: next read, end of current set, next write
-        uint32_t flo = 0, fhi = 0;                      // 64-bit membership filter of this step's new entries
-        bool ovf = false;
+        uint32_t pcls = 0;                              // cls1 of the previous symbol if state A fired on it
         uint32_t ovf_at = 0;
-        if (nsteps) {
-            if (h.start_id < nsb) {                                                   // Design/FPGA.v:146-147
+        // ---- warp-uniform state ----
+        uint32_t ncur = 0, nnew = 0;                    // items in cur / nxt
+        uint32_t ovfm = 0;                              // lanes whose stream was handed to the general kernel
+        filt[lane] = 0;
+        {   // S_0 = {0}  (Design/FPGA.v:146-147)
+            const bool in_list = nsteps != 0 && h.start_id >= nsb;
+            if (nsteps != 0 && h.start_id < nsb) {
                 if (W == 1 || h.start_id < 64) P0 = 1ull << (h.start_id & 63); else P1 = 1ull << (h.start_id & 63);
-            } else { *reinterpret_cast<uint16_t *>(lb) = (uint16_t)h.start_id; re = ROW; wp = ROW; }
+            }
+            const uint32_t m = __ballot_sync(FULL, in_list);
+            if (in_list) cur[__popc(m & ltmask)] = (lane << 16) | h.start_id;
+            ncur = __popc(m);
         }
         // input: aligned 16-byte chunks kept in registers, the first one shifted to the stream's first byte
         uint64_t blo = 0, bhi = 0, plo = 0, phi = 0;
@@ -142,9 +175,67 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             }
             nextp += 16;
         }
+        __syncwarp();
+
+        // Adds (owner o, target t) of every lane with `hit` to S_{k+1}.  Converged; all lanes call it.
+        auto warp_push = [&](bool hit, uint32_t o, uint32_t t) {
+            if (!__any_sync(FULL, hit)) return;
+            // targets that are sticky states: set the bit in the owner's Pn (rare)
+            uint32_t sm = __ballot_sync(FULL, hit && t < nsb);
+            while (sm) {
+                const int src = __ffs((int)sm) - 1;
+                sm &= sm - 1;
+                const uint32_t oo = __shfl_sync(FULL, o, src), tt = __shfl_sync(FULL, t, src);
+                if (lane == oo) { if (W == 1 || tt < 64) Pn0 |= 1ull << (tt & 63); else Pn1 |= 1ull << (tt & 63); }
+            }
+            const bool tr = hit && t >= nsb;
+            const uint32_t key = (o << 16) | t;
+            // membership filter: a clear bit proves the key is new in this step
+            const uint32_t hsh10 = (t ^ (o * 0x9Du)) & 1023u;
+            const uint32_t fbit = 1u << (hsh10 & 31);
+            uint32_t old = 0;
+            if (tr) old = atomicOr(&filt[hsh10 >> 5], fbit);
+            const bool maybe = tr && (old & fbit);
+            const bool fresh = tr && !maybe;
+            uint32_t am = __ballot_sync(FULL, fresh);
+            uint32_t pos = nnew + __popc(am & ltmask);
+            bool spill = fresh && pos >= wcap;
+            if (fresh && pos < wcap) nxt[pos] = key;
+            nnew = min(nnew + __popc(am), wcap);
+            if (__any_sync(FULL, maybe)) {   // exact check against everything collected so far in this step
+                __syncwarp();
+                bool found = false;
+                if (maybe) for (uint32_t j = 0; j < nnew; j++) found |= nxt[j] == key;
+                const bool cand = maybe && !found;
+                const uint32_t cmk = __ballot_sync(FULL, cand);
+                bool lead = false;
+                if (cand) { const uint32_t grp = __match_any_sync(cmk, key); lead = (uint32_t)(__ffs((int)grp) - 1) == lane; }
+                am = __ballot_sync(FULL, lead);
+                pos = nnew + __popc(am & ltmask);
+                spill = spill || (lead && pos >= wcap);
+                if (lead && pos < wcap) nxt[pos] = key;
+                nnew = min(nnew + __popc(am), wcap);
+            }
+            uint32_t om = __ballot_sync(FULL, spill);   // list full: those owners go to the general kernel
+            while (om) {
+                const int src = __ffs((int)om) - 1;
+                om &= om - 1;
+                ovfm |= 1u << __shfl_sync(FULL, o, src);
+            }
+        };
+        // appends one own-stream item per lane with `has` to the current list
+        auto append_cur = [&](bool has, uint32_t item) {
+            const uint32_t m = __ballot_sync(FULL, has);
+            const uint32_t pos = ncur + __popc(m & ltmask);
+            if (has) { if (pos < wcap) cur[pos] = item; else ovfm |= 0u; }
+            const uint32_t om = __ballot_sync(FULL, has && pos >= wcap);
+            ovfm |= om;                                   // own item did not fit: owner == lane
+            ncur = min(ncur + __popc(m), wcap);
+        };
 
         for (uint32_t k = 0; k < maxsteps; k++) {
-            const bool act = k < nsteps && !ovf;
+            const uint32_t livem = __ballot_sync(FULL, k < nsteps) & ~ovfm;   // streams still being scanned here
+            const bool act = (livem >> lane) & 1u;
             // ---- next symbol ----
             if (bufn == 0) {
                 blo = plo; bhi = phi; bufn = 16;
@@ -160,11 +251,17 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             bhi >>= 8;
             bufn--;
             const uint32_t hf = ((c * hmul) >> hsh) & 0xFFu;   // symbol hash; a row uses its low bits
-            const uint32_t hc = hf & nbm;
 
-            // ---- sticky states: survivors P & K[c]; those in P & M[c] fire their rows below ----
+            // ---- own-stream items of this step: two-symbol table hits and firing sticky rows ----
+            uint32_t x = 0xFFFFu;
+            if (accel) {
+                const uint32_t cm = cmap[c];
+                x = t2[pcls * nc2 + (cm >> 8)];
+                pcls = (act && (P0 & 1ull)) ? (cm & 0xFFu) : 0u;
+                if (!act) x = 0xFFFFu;
+            }
             uint64_t im0 = 0, im1 = 0;
-            if (act) {
+            if (act) {   // sticky states: survivors P & K[c]; those in P & M[c] fire their rows
                 const uint8_t *mrow = mask + c * MSTRIDE;
                 bool attn;
                 if (W == 1) attn = (P0 & *reinterpret_cast<const uint64_t *>(mrow)) != 0;
@@ -187,76 +284,77 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     }
                 }
             }
-
-            // ---- expand S_k: one edge-table lookup per lane per iteration -------------------------------
-            // work items of a lane: its transient states (ring) and the rows of its firing sticky states
-            bool walking = false;
-            uint32_t idx = 0;
-            bool work = act && (rp != re || (im0 | im1) != 0);
-            while (__any_sync(FULL, work)) {
-                if (work) {
-                    bool look = true;
-                    if (!walking) {
-                        if (rp != re) {
-                            const uint32_t u = *reinterpret_cast<const uint16_t *>(lb + rp);
-                            rp = (rp + ROW) & RMASK;
-                            if (u - acc_base < n_acc) {   // accepting state found in S_k (Design/FPGA.v:210-226)
-                                emit_match(out, sid + batch.stream_id_base, k, nfa.orig_of_id[u]);
-                                look = false;
-                            } else idx = u + (u >= gbase ? hc : 0u);
-                        } else {
-                            uint32_t bit;
-                            if (W == 1 || im0) { bit = (uint32_t)__ffsll((long long)im0) - 1u; im0 &= im0 - 1; }
-                            else { bit = 63u + (uint32_t)__ffsll((long long)im1); im1 &= im1 - 1; }
-                            const uint32_t d = sdesc[bit];
-                            idx = (d & 0xFFFFu) + (hf & (d >> 16));
-                        }
+            uint32_t tq = 0;   // cursor into a multi-target list of the two-symbol table
+            while (__any_sync(FULL, x != 0xFFFFu || (im0 | im1) != 0)) {
+                bool has = false;
+                uint32_t item = 0;
+                if (x != 0xFFFFu) {
+                    has = true;
+                    if (x < 0x8000u) { item = ITEM_DIRECT | (lane << 16) | x; x = 0xFFFFu; }
+                    else {
+                        if (tq == 0) tq = x & 0x7FFFu;
+                        const uint32_t tl = tl2[tq++];
+                        item = ITEM_DIRECT | (lane << 16) | (tl & 0x7FFFu);
+                        if (!(tl & 0x8000u)) { x = 0xFFFFu; tq = 0; }
                     }
-                    if (look) {
+                } else if ((im0 | im1) != 0) {
+                    uint32_t bit;
+                    if (W == 1 || im0) { bit = (uint32_t)__ffsll((long long)im0) - 1u; im0 &= im0 - 1; }
+                    else { bit = 63u + (uint32_t)__ffsll((long long)im1); im1 &= im1 - 1; }
+                    const uint32_t d = sdesc[bit];
+                    has = true;
+                    item = ITEM_ROW | (lane << 16) | ((d & 0xFFFFu) + (hf & (d >> 16)));
+                }
+                append_cur(has, item);
+            }
+            __syncwarp();
+
+            // ---- expand S_k: 32 items per round, one edge-table lookup per lane ----
+            for (uint32_t rd = 0; rd < ncur; rd += 32) {
+                const uint32_t i = rd + lane;
+                const uint32_t ent = i < ncur ? cur[i] : 0u;
+                const uint32_t o = (ent >> 16) & 31u;
+                const uint32_t co = __shfl_sync(FULL, c, o);          // the owner's current symbol
+                const uint32_t val = ent & 0xFFFFu;
+                bool hit = false, walking = false;
+                uint32_t t = 0, idx = 0;
+                if (i < ncur && ((livem >> o) & 1u)) {
+                    if (ent & ITEM_DIRECT) { hit = true; t = val; }
+                    else if (ent & ITEM_ROW) { idx = val; walking = true; }
+                    else if (val - acc_base < n_acc)                  // accepting state in S_k (Design/FPGA.v:210-226)
+                        emit_match_cold(out, base + o + batch.stream_id_base, k, nfa.orig_of_id[val]);
+                    else { idx = val + (val >= gbase ? (((co * hmul) >> hsh) & nbm) : 0u); walking = true; }
+                }
+                for (;;) {
+                    if (walking) {
                         const uint32_t e = tab[idx];
-                        const uint32_t a = e & 0xFFu, b = (e >> 8) & 0xFFu, t = (e >> 16) & 0x7FFFu;
-                        bool hit;
+                        const uint32_t a = e & 0xFFu, b = (e >> 8) & 0xFFu;
+                        t = (e >> 16) & 0x7FFFu;
                         walking = (e & TAB_MORE) != 0;
                         idx++;
-                        if (a <= b) hit = (c == a) | (c == b);
+                        if (a <= b) hit = (co == a) | (co == b);
                         else if (a == 0xFFu) { hit = false; idx = t; walking = true; }      // indirect -> chain
-                        else hit = (memb[((0xFEu - a) * 253u + b) * 8 + (c >> 5)] >> (c & 31)) & 1u;
-                        if (hit && !ovf) {
-                            if (t < nsb) {                                               // entering a sticky state
-                                const uint64_t sb = 1ull << (t & 63);
-                                if (W == 1 || t < 64) Pn0 |= sb; else Pn1 |= sb;
-                            } else {
-                                const uint32_t fb = 1u << (t & 31);
-                                const bool fh = (t & 32) != 0;
-                                bool dup = false;
-                                if ((fh ? fhi : flo) & fb) {   // possible duplicate: exact check of this step's new entries
-                                    for (uint32_t o = re; o != wp; o = (o + ROW) & RMASK)
-                                        if (*reinterpret_cast<const uint16_t *>(lb + o) == t) { dup = true; break; }
-                                }
-                                if (!dup) {
-                                    const uint32_t nw = (wp + ROW) & RMASK;
-                                    if (nw == rp) ovf = true;                            // ring full: hand the stream over
-                                    else {
-                                        *reinterpret_cast<uint16_t *>(lb + wp) = (uint16_t)t;
-                                        wp = nw;
-                                        if (fh) fhi |= fb; else flo |= fb;
-                                    }
-                                }
-                            }
-                        }
+                        else hit = (memb[((0xFEu - a) * 253u + b) * 8 + (co >> 5)] >> (co & 31)) & 1u;
                     }
-                    work = walking || rp != re || (im0 | im1) != 0;
+                    warp_push(hit, o, t);
+                    hit = false;
+                    if (!__any_sync(FULL, walking)) break;
                 }
             }
 
-            if (act) {   // current <= next (Design/FPGA.v:733-737)
+            // ---- current <= next (Design/FPGA.v:733-737) ----
+            __syncwarp();
+            if (act) {
                 P0 |= Pn0; Pn0 = 0;
                 if (W == 2) { P1 |= Pn1; Pn1 = 0; }
-                re = wp; flo = 0; fhi = 0;
-                if (ovf) ovf_at = k + 1;   // S_k was fully examined; the general kernel reports from step k+1 on
+                if ((ovfm >> lane) & 1u) ovf_at = k + 1;   // S_k was fully examined; the general kernel reports from k+1 on
             }
+            { uint32_t *tmp = cur; cur = nxt; nxt = tmp; }
+            ncur = nnew; nnew = 0;
+            filt[lane] = 0;
+            __syncwarp();
         }
-        if (ovf && ovf_at < nsteps) {
+        if (((ovfm >> lane) & 1u) && ovf_at < nsteps) {
             const unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
             out.rescan[slot] = make_uint2(sid, ovf_at);
         }
@@ -270,11 +368,13 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
 }
 
 cudaError_t launch_scan_lane(const NfaDev &nfa, const BatchDev &batch, const OutDev &out, int n_sms, cudaStream_t stream) {
-    const size_t smem = lane_smem_bytes(nfa.h);
+    const uint32_t wcap = lane_wcap_for(nfa.h);
+    if (wcap < 64) return cudaErrorInvalidValue;
+    const size_t smem = lane_smem_bytes(nfa.h, wcap);
     unsigned long long want = (batch.n_streams + LANE_THREADS - 1) / LANE_THREADS;
     int grid = (int)(want < (unsigned long long)n_sms ? (want ? want : 1) : (unsigned long long)n_sms);
-    if (nfa.h.sticky_words == 1) scan_lane_kernel<1><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out);
-    else scan_lane_kernel<2><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out);
+    if (nfa.h.sticky_words == 1) scan_lane_kernel<1><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out, wcap);
+    else scan_lane_kernel<2><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out, wcap);
     return cudaGetLastError();
 }
 

@@ -19,7 +19,7 @@ static uint64_t splitmix64(uint64_t x) {
     return z ^ (z >> 31);
 }
 
-struct Stats { double entries = 0, lookups = 0, indirect = 0, cls = 0, pushes = 0, attn = 0, inj = 0, sticky = 0, symbols = 0, maxlist = 0; };
+struct Stats { double t2hits = 0, entries = 0, lookups = 0, indirect = 0, cls = 0, pushes = 0, attn = 0, inj = 0, sticky = 0, symbols = 0, maxlist = 0; };
 
 int main(int argc, char **argv) {
     if (argc < 4) return 1;
@@ -43,6 +43,8 @@ int main(int argc, char **argv) {
         uint64_t off = splitmix64(0x5EED0001ull ^ (uint64_t)j) % (std::min(lo.size(), hi.size()) - L + 1);
         Stats &s = st[j & 1];
         uint64_t P[2] = {0, 0};
+        uint32_t pcls = 0;
+        const uint16_t *cmap = (const uint16_t *)&img.blob[h.off_cmap], *t2 = (const uint16_t *)&img.blob[h.off_t2], *tl2 = (const uint16_t *)&img.blob[h.off_tl2];
         std::vector<uint32_t> cur, nxt;
         if (h.start_id < h.nsb) P[h.start_id >> 6] |= 1ull << (h.start_id & 63); else cur.push_back(h.start_id);
         for (uint32_t k = 0; k < L; k++) {
@@ -62,6 +64,11 @@ int main(int argc, char **argv) {
                     idx++;
                 }
             };
+            if (h.accel) {
+                uint32_t cm = cmap[c], x = t2[pcls * h.nc2 + (cm >> 8)];
+                pcls = (P[0] & 1) ? (cm & 0xFF) : 0;
+                if (x != 0xFFFF) { s.t2hits++; if (x < 0x8000) push(x); else for (uint32_t q = x & 0x7FFF;; q++) { push(tl2[q] & 0x7FFF); if (!(tl2[q] & 0x8000)) break; } }
+            }
             s.entries += cur.size(); per_sym_entries[j][k] = cur.size();
             s.maxlist = std::max<double>(s.maxlist, cur.size());
             const uint64_t *A = (const uint64_t *)&img.blob[h.off_mask + c * ms];
@@ -84,7 +91,7 @@ int main(int argc, char **argv) {
     }
     for (int t = 0; t < 2; t++) {
         Stats &s = st[t];
-        printf("%s: per symbol: entries %.3f lookups %.3f indirect %.3f class %.3f pushes %.3f attn %.3f inj %.3f sticky %.2f maxlist %.0f\n", t ? "hi" : "lo",
+        printf("%s: per symbol: t2hits %.3f entries %.3f lookups %.3f indirect %.3f class %.3f pushes %.3f attn %.3f inj %.3f sticky %.2f maxlist %.0f\n", t ? "hi" : "lo", s.t2hits / s.symbols,
                s.entries / s.symbols, s.lookups / s.symbols, s.indirect / s.symbols, s.cls / s.symbols, s.pushes / s.symbols, s.attn / s.symbols, s.inj / s.symbols, s.sticky / s.symbols, s.maxlist);
     }
     // lock-step warp bound: mean over (warp, symbol) of max over its 32 lanes
