@@ -196,7 +196,7 @@ def run_e2e(args, torch, dist, nfa, batch, n, first, cap, n_states, n_matches, b
 def ours_arm(args, rank, world, local_rank):
     import torch
     import regex_fpga_b200 as R
-    from regex_fpga_b200 import workloads as WL
+    from regex_fpga_b200 import shard, workloads as WL
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the scan has no CPU path (use --impl reference for the CPU arm)")
@@ -224,7 +224,7 @@ def ours_arm(args, rank, world, local_rank):
                             recs.data_ptr(), cap, flags=R.SCAN_ASYNC, cuda_stream=stream.cuda_stream,
                             stream_id_base=first)
         if dist is not None:
-            dist.all_reduce(counts)          # final exchange of the path: per-state match counts
+            shard.reduce_counts(counts, dist)   # the path's only exchange: per-state match counts (NCCL)
         return r
 
     def barrier():
