@@ -89,8 +89,8 @@ static ImageOptions default_image_options() {
     if (const char *s = std::getenv("RFB_STICKY_WORDS")) opt.sticky_words = std::atoi(s);
     if (const char *s = std::getenv("RFB_BUCKET_BITS")) opt.bucket_bits = std::atoi(s);
     if (const char *s = std::getenv("RFB_STICKY_MIN_SELF")) opt.sticky_min_self = std::atoi(s);
-    // leave room for two 64-item lists and the filter of every warp beside the tables
-    opt.max_bytes = (uint32_t)(MAX_DYN_SMEM - (LANE_THREADS / 32) * (2 * 64 * 4 + 32 * 4) - 64);
+    // the per-stream rings (16 entries x 1024 streams x 2 bytes) share the SM's shared memory with the tables
+    opt.max_bytes = (uint32_t)(MAX_DYN_SMEM - 16 * LANE_THREADS * 2 - 64);
     return opt;
 }
 

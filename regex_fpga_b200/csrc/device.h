@@ -50,8 +50,7 @@ constexpr int LANE_THREADS = 1024;   // one CTA per SM
 constexpr int WARP_THREADS = 256;
 constexpr int WARP_LCAP = 512;       // sparse list entries per warp before it switches to bitmap scans
 
-size_t lane_smem_bytes(const ImageHeader &h, uint32_t wcap);
-uint32_t lane_wcap_for(const ImageHeader &h);   // items per warp-shared list that fit beside the image
+size_t lane_smem_bytes(const ImageHeader &h);
 size_t warp_smem_bytes(uint32_t n_states, int warps_per_cta);
 
 // Enqueue the lane kernel (one thread per stream, tables in shared memory).

@@ -68,333 +68,15 @@ __device__ __forceinline__ void stage_image(uint8_t *dst, const uint8_t *src, ui
 // ------------------------------------------------------------------------------------------------
 // lane kernel
 // ------------------------------------------------------------------------------------------------
+constexpr int RING_CAP = 16;   // ring entries per stream (power of two)
 
-// out-of-line copy for the lane kernel's hot loop (matches are rare there)
+size_t lane_smem_bytes(const ImageHeader &h) { return (size_t)h.blob_bytes + (size_t)RING_CAP * LANE_THREADS * 2 + 16; }
+
+// out-of-line copies for the lane kernel's hot loop (both are rare there)
 __device__ __noinline__ void emit_match_cold(const OutDev &out, uint32_t stream, uint32_t pos, uint32_t state) {
     emit_match(out, stream, pos, state);
 }
-
-// Work items of the warp-shared list: owner lane in bits 16..20, 16-bit value in bits 0..15.
-//   kind STATE  : value = internal state id (a member of S_k; accept ids are reported, others looked up)
-//   kind ROW    : value = edge-table index already hashed (row of a firing sticky state)
-constexpr uint32_t ITEM_ROW = 1u << 30;
-constexpr uint32_t LANE_FILT_WORDS = 32;   // 1024-bit membership filter per warp
-
-size_t lane_smem_bytes(const ImageHeader &h, uint32_t wcap) {
-    const size_t warps = LANE_THREADS / 32;
-    return (size_t)h.blob_bytes + warps * (2 * (size_t)wcap * 4 + LANE_FILT_WORDS * 4) + 16;
-}
-uint32_t lane_wcap_for(const ImageHeader &h) {
-    const size_t warps = LANE_THREADS / 32;
-    const size_t avail = MAX_DYN_SMEM - h.blob_bytes - warps * LANE_FILT_WORDS * 4 - 64;
-    size_t wcap = avail / (warps * 8);
-    wcap = wcap / 32 * 32;
-    return (uint32_t)(wcap > 512 ? 512 : wcap);
-}
-
-template <int W>
-__global__ void __launch_bounds__(LANE_THREADS, 1)
-scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const uint32_t wcap) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const ImageHeader &h = nfa.h;
-    constexpr uint32_t WARPS = LANE_THREADS / 32;
-    constexpr uint32_t FULL = 0xffffffffu;
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const uint32_t ltmask = (1u << lane) - 1u;
-    uint32_t *wl_base = reinterpret_cast<uint32_t *>(smem + h.blob_bytes);
-    uint32_t *cur = wl_base + (size_t)warp * 2 * wcap;       // items of S_k (plus this step's sticky-row items)
-    uint32_t *nxt = cur + wcap;                              // members of S_{k+1} being collected
-    uint32_t *filt = wl_base + (size_t)WARPS * 2 * wcap + warp * LANE_FILT_WORDS;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + h.blob_bytes + (size_t)WARPS * (2 * (size_t)wcap * 4 + LANE_FILT_WORDS * 4));
-    stage_image(smem, nfa.blob, h.blob_bytes, bar);
-
-    const uint32_t *tab = reinterpret_cast<const uint32_t *>(smem + h.off_tab);
-    const uint8_t *mask = smem + h.off_mask;
-    const uint32_t *memb = reinterpret_cast<const uint32_t *>(smem + h.off_memb);
-    const uint32_t *sdesc = reinterpret_cast<const uint32_t *>(smem + h.off_sdesc);
-    const uint16_t *cmap = reinterpret_cast<const uint16_t *>(smem + h.off_cmap);
-    const uint16_t *t2 = reinterpret_cast<const uint16_t *>(smem + h.off_t2);
-    const uint16_t *tl2 = reinterpret_cast<const uint16_t *>(smem + h.off_tl2);
-    const uint32_t gbase = h.gbase, nsb = h.nsb, hmul = h.hash_mul, hsh = h.hash_shift;
-    const uint32_t nbm = (1u << h.bucket_bits) - 1u;
-    const uint32_t acc_base = h.acc_base, n_acc = h.n_acc, nc2 = h.nc2;
-    const bool accel = h.accel != 0;
-    constexpr uint32_t MSTRIDE = 32u * W;
-
-    // A warp takes 32 consecutive streams at a time (one per lane) and steps them in lock-step.  The
-    // transient members of all 32 current sets live in ONE warp-shared list, so that the edge-table
-    // lookups of a step are spread over all lanes no matter how unevenly the streams are loaded.
-    for (;;) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(&out.g->next_stream, 32u);
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= batch.n_streams) break;
-        const uint32_t sid = base + lane;
-        const bool valid = sid < batch.n_streams;
-        const uint32_t nsteps = valid ? (batch.steps ? batch.steps[sid] : batch.n_steps) : 0u;
-        const uint32_t maxsteps = __reduce_max_sync(FULL, nsteps);
-
-        // ---- per-lane stream state ----
-        uint64_t P0 = 0, P1 = 0, Pn0 = 0, Pn1 = 0;      // sticky sets (P1/Pn1 unused when W == 1)
-        uint32_t pcls = 0;                              // cls1 of the previous symbol if state A fired on it
-        uint32_t ovf_at = 0;
-        // ---- warp-uniform state ----
-        uint32_t ncur = 0, nnew = 0;                    // items in cur / nxt
-        uint32_t ovfm = 0;                              // lanes whose stream was handed to the general kernel
-        filt[lane] = 0;
-        {   // S_0 = {0}  (Design/FPGA.v:146-147)
-            const bool in_list = nsteps != 0 && h.start_id >= nsb;
-            if (nsteps != 0 && h.start_id < nsb) {
-                if (W == 1 || h.start_id < 64) P0 = 1ull << (h.start_id & 63); else P1 = 1ull << (h.start_id & 63);
-            }
-            const uint32_t m = __ballot_sync(FULL, in_list);
-            if (in_list) cur[__popc(m & ltmask)] = (lane << 16) | h.start_id;
-            ncur = __popc(m);
-        }
-        // input: aligned 16-byte chunks kept in registers, the first one shifted to the stream's first byte
-        uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;        // remaining bytes of the current chunk, next byte in b0[7:0]
-        uint4 pre = make_uint4(0, 0, 0, 0);             // the chunk after it
-        uint32_t bufn = 16;
-        const uint8_t *nextp = nullptr, *endp = nullptr;
-        if (nsteps) {
-            const uint8_t *sp = stream_ptr(batch, sid);
-            endp = sp + nsteps;
-            const uint8_t *b16 = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15);
-            const uint32_t off = (uint32_t)(sp - b16);
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(b16));
-            b0 = v.x; b1 = v.y; b2 = v.z; b3 = v.w;
-            for (uint32_t q = 0; q < off; q++) {        // once per stream; off == 0 for aligned batches
-                b0 = __funnelshift_r(b0, b1, 8); b1 = __funnelshift_r(b1, b2, 8); b2 = __funnelshift_r(b2, b3, 8); b3 >>= 8;
-            }
-            bufn = 16 - off;
-            nextp = b16 + 16;
-            if (nextp < endp) pre = __ldg(reinterpret_cast<const uint4 *>(nextp));
-            nextp += 16;
-        }
-        __syncwarp();
-
-        // marks the owners of items that did not fit as handed over to the general kernel (rare)
-        auto spill_owners = [&](bool spill, uint32_t o) {
-            uint32_t om = __ballot_sync(FULL, spill);
-            while (om) {
-                const int src = __ffs((int)om) - 1;
-                om &= om - 1;
-                ovfm |= 1u << __shfl_sync(FULL, o, src);
-            }
-        };
-        // Adds (owner o, target t) of every lane with `hit` to S_{k+1}.  Converged; all lanes call it.
-        auto warp_push = [&](bool hit, uint32_t o, uint32_t t) {
-            if (!__any_sync(FULL, hit)) return;
-            const bool st = hit && t < nsb;             // targets that are sticky states: bit in the owner's Pn (rare)
-            uint32_t sm = __ballot_sync(FULL, st);
-            while (sm) {
-                const int src = __ffs((int)sm) - 1;
-                sm &= sm - 1;
-                const uint32_t oo = __shfl_sync(FULL, o, src), tt = __shfl_sync(FULL, t, src);
-                if (lane == oo) { if (W == 1 || tt < 64) Pn0 |= 1ull << (tt & 63); else Pn1 |= 1ull << (tt & 63); }
-            }
-            const bool tr = hit && !st;
-            const uint32_t key = (o << 16) | t;
-            // membership filter: a clear bit proves the key is new in this step
-            const uint32_t hsh10 = (t ^ (o * 0x9Du)) & 1023u;
-            const uint32_t fbit = 1u << (hsh10 & 31);
-            uint32_t old = 0;
-            if (tr) old = atomicOr(&filt[hsh10 >> 5], fbit);
-            const bool maybe = tr && (old & fbit);
-            const bool fresh = tr && !maybe;
-            uint32_t am = __ballot_sync(FULL, fresh);
-            uint32_t pos = nnew + __popc(am & ltmask);
-            bool spill = fresh && pos >= wcap;
-            if (fresh && pos < wcap) nxt[pos] = key;
-            nnew = min(nnew + __popc(am), wcap);
-            uint32_t mm = __ballot_sync(FULL, maybe);
-            if (mm) {   // exact check against everything collected so far in this step, one key at a time, all lanes scanning
-                __syncwarp();
-                uint32_t dupm = 0;
-                for (uint32_t m2 = mm; m2; m2 &= m2 - 1) {
-                    const int src = __ffs((int)m2) - 1;
-                    const uint32_t kk = __shfl_sync(FULL, key, src);
-                    bool f = false;
-                    for (uint32_t j = lane; j < nnew; j += 32) f |= nxt[j] == kk;
-                    if (__any_sync(FULL, f)) dupm |= 1u << src;
-                }
-                const bool cand = maybe && !((dupm >> lane) & 1u);
-                const uint32_t cmk = __ballot_sync(FULL, cand);
-                bool lead = false;
-                if (cand) { const uint32_t grp = __match_any_sync(cmk, key); lead = (uint32_t)(__ffs((int)grp) - 1) == lane; }
-                am = __ballot_sync(FULL, lead);
-                pos = nnew + __popc(am & ltmask);
-                spill = spill || (lead && pos >= wcap);
-                if (lead && pos < wcap) nxt[pos] = key;
-                nnew = min(nnew + __popc(am), wcap);
-            }
-            if (__any_sync(FULL, spill)) spill_owners(spill, o);
-        };
-        // appends one item per lane with `has` to the current list (owner o)
-        auto append_cur = [&](bool has, uint32_t item, uint32_t o) {
-            const uint32_t m = __ballot_sync(FULL, has);
-            if (!m) return;
-            const uint32_t pos = ncur + __popc(m & ltmask);
-            if (has && pos < wcap) cur[pos] = item;
-            if (ncur + __popc(m) > wcap) spill_owners(has && pos >= wcap, o);
-            ncur = min(ncur + __popc(m), wcap);
-        };
-        // a two-symbol-table target of this lane's own stream goes straight into S_{k+1}: within this phase
-        // all keys are distinct (one owner per lane, distinct targets per list), so no exact check is needed
-        auto push_own = [&](bool has, uint32_t t) {
-            const bool st = has && t < nsb;
-            if (st) { if (W == 1 || t < 64) Pn0 |= 1ull << (t & 63); else Pn1 |= 1ull << (t & 63); }
-            const bool tr = has && !st;
-            const uint32_t m = __ballot_sync(FULL, tr);
-            if (!m) return;
-            const uint32_t hsh10 = (t ^ (lane * 0x9Du)) & 1023u;
-            if (tr) atomicOr(&filt[hsh10 >> 5], 1u << (hsh10 & 31));
-            const uint32_t pos = nnew + __popc(m & ltmask);
-            if (tr && pos < wcap) nxt[pos] = (lane << 16) | t;
-            if (nnew + __popc(m) > wcap) spill_owners(tr && pos >= wcap, lane);
-            nnew = min(nnew + __popc(m), wcap);
-        };
-
-        for (uint32_t k = 0; k < maxsteps; k++) {
-            const uint32_t livem = __ballot_sync(FULL, k < nsteps) & ~ovfm;   // streams still being scanned here
-            const bool act = (livem >> lane) & 1u;
-            // ---- next symbol ----
-            if (bufn == 0) {
-                b0 = pre.x; b1 = pre.y; b2 = pre.z; b3 = pre.w; bufn = 16;
-                if (nextp < endp) pre = __ldg(reinterpret_cast<const uint4 *>(nextp));
-                nextp += 16;
-            }
-            const uint32_t c = b0 & 0xFFu;
-            b0 = __funnelshift_r(b0, b1, 8); b1 = __funnelshift_r(b1, b2, 8); b2 = __funnelshift_r(b2, b3, 8); b3 >>= 8;
-            bufn--;
-            const uint32_t hf = ((c * hmul) >> hsh) & 0xFFu;   // symbol hash; a row uses its low bits
-
-            // ---- two-symbol start table: successors of the never-materialised targets of state A ----
-            if (accel) {
-                const uint32_t cm = cmap[c];
-                uint32_t x = t2[pcls * nc2 + (cm >> 8)];
-                pcls = (act && (P0 & 1ull)) ? (cm & 0xFFu) : 0u;
-                if (!act) x = 0xFFFFu;
-                push_own(x < 0x8000u, x);
-                if (__any_sync(FULL, x >= 0x8000u && x != 0xFFFFu)) {   // several targets (rare)
-                    uint32_t q = (x >= 0x8000u && x != 0xFFFFu) ? (x & 0x7FFFu) : 0xFFFFFFFFu;
-                    while (__any_sync(FULL, q != 0xFFFFFFFFu)) {
-                        const bool has = q != 0xFFFFFFFFu;
-                        const uint32_t tl = has ? tl2[q] : 0u;
-                        push_own(has, tl & 0x7FFFu);
-                        q = (has && (tl & 0x8000u)) ? q + 1 : 0xFFFFFFFFu;
-                    }
-                }
-            }
-
-            // ---- sticky states: survivors P & K[c]; those in P & M[c] fire their rows (as list items) ----
-            {
-                uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;     // firing bits, 32 per word
-                if (act) {
-                    const uint8_t *mrow = mask + c * MSTRIDE;
-                    bool attn;
-                    if (W == 1) attn = (P0 & *reinterpret_cast<const uint64_t *>(mrow)) != 0;
-                    else {
-                        const uint4 a = *reinterpret_cast<const uint4 *>(mrow);
-                        attn = (((uint32_t)P0 & a.x) | ((uint32_t)(P0 >> 32) & a.y) | ((uint32_t)P1 & a.z) | ((uint32_t)(P1 >> 32) & a.w)) != 0;
-                    }
-                    if (attn) {
-                        if (W == 1) {
-                            const uint4 km = *reinterpret_cast<const uint4 *>(mrow + 16);
-                            i0 = (uint32_t)P0 & km.z; i1 = (uint32_t)(P0 >> 32) & km.w;
-                            P0 &= (uint64_t)km.x | ((uint64_t)km.y << 32);
-                        } else {
-                            const uint4 kk = *reinterpret_cast<const uint4 *>(mrow + 16);
-                            const uint4 mm = *reinterpret_cast<const uint4 *>(mrow + 32);
-                            i0 = (uint32_t)P0 & mm.x; i1 = (uint32_t)(P0 >> 32) & mm.y;
-                            i2 = (uint32_t)P1 & mm.z; i3 = (uint32_t)(P1 >> 32) & mm.w;
-                            P0 &= (uint64_t)kk.x | ((uint64_t)kk.y << 32);
-                            P1 &= (uint64_t)kk.z | ((uint64_t)kk.w << 32);
-                        }
-                    }
-                }
-                while (__any_sync(FULL, (i0 | i1 | i2 | i3) != 0)) {
-                    const bool has = (i0 | i1 | i2 | i3) != 0;
-                    uint32_t wsel, wbase;
-                    if (i0) { wsel = i0; wbase = 0; i0 &= i0 - 1; }
-                    else if (i1) { wsel = i1; wbase = 32; i1 &= i1 - 1; }
-                    else if (i2) { wsel = i2; wbase = 64; i2 &= i2 - 1; }
-                    else { wsel = i3; wbase = 96; i3 &= i3 - 1; }
-                    uint32_t item = 0;
-                    if (has) {
-                        const uint32_t d = sdesc[wbase + (uint32_t)__ffs((int)wsel) - 1u];
-                        item = ITEM_ROW | (lane << 16) | ((d & 0xFFFFu) + (hf & (d >> 16)));
-                    }
-                    append_cur(has, item, lane);
-                }
-            }
-            __syncwarp();
-
-            // ---- expand S_k: 32 items per round, one edge-table lookup per lane ----
-            for (uint32_t rd = 0; rd < ncur;) {
-                const uint32_t rend = min(rd + 32u, ncur);            // chains append behind rend while we work
-                const uint32_t i = rd + lane;
-                const uint32_t ent = i < rend ? cur[i] : 0u;
-                const uint32_t o = (ent >> 16) & 31u;
-                const uint32_t co = __shfl_sync(FULL, c, o);          // the owner's current symbol
-                const uint32_t val = ent & 0xFFFFu;
-                const bool isrow = (ent & ITEM_ROW) != 0;
-                bool look = i < rend && ((livem >> o) & 1u);
-                if (look && !isrow && val - acc_base < n_acc) {       // accepting state in S_k (Design/FPGA.v:210-226)
-                    emit_match_cold(out, base + o + batch.stream_id_base, k, nfa.orig_of_id[val]);
-                    look = false;
-                }
-                const uint32_t idx = val + ((!isrow && val >= gbase) ? (((co * hmul) >> hsh) & nbm) : 0u);
-                bool hit = false, cont = false;
-                uint32_t t = 0, nidx = idx + 1;
-                if (look) {
-                    const uint32_t e = tab[idx];
-                    const uint32_t a = e & 0xFFu, b = (e >> 8) & 0xFFu;
-                    t = (e >> 16) & 0x7FFFu;
-                    cont = (e & TAB_MORE) != 0;
-                    if (a <= b) hit = (co == a) | (co == b);
-                    else if (a == 0xFFu) { nidx = t; cont = true; }                      // indirect -> chain
-                    else hit = (memb[((0xFEu - a) * 253u + b) * 8 + (co >> 5)] >> (co & 31)) & 1u;
-                }
-                warp_push(hit, o, t);
-                append_cur(cont, ITEM_ROW | (o << 16) | nidx, o);     // chains continue as new items of this step
-                __syncwarp();
-                rd = rend;
-            }
-
-            // ---- current <= next (Design/FPGA.v:733-737) ----
-            if (act) {
-                P0 |= Pn0; Pn0 = 0;
-                if (W == 2) { P1 |= Pn1; Pn1 = 0; }
-                if ((ovfm >> lane) & 1u) ovf_at = k + 1;   // S_k was fully examined; the general kernel reports from k+1 on
-            }
-            { uint32_t *tmp = cur; cur = nxt; nxt = tmp; }
-            ncur = nnew; nnew = 0;
-            filt[lane] = 0;
-            __syncwarp();
-        }
-        if (((ovfm >> lane) & 1u) && ovf_at < nsteps) {
-            const unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
-            out.rescan[slot] = make_uint2(sid, ovf_at);
-        }
-        if (batch.steps) {
-            unsigned long long tot = nsteps;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
-            if (lane == 0) atomicAdd(&out.g->n_symbols, tot);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// lane kernel, per-lane ring variant: same per-symbol semantics, but every lane keeps the transient
-// members of its own stream in a private ring in shared memory and expands them itself (no warp-level
-// work sharing; one vote per inner iteration).  Kept as a measured alternative (RFB_LANE_MODE=ring).
-// ------------------------------------------------------------------------------------------------
-constexpr int RING_CAP = 16;   // ring entries per stream (power of two)
-
-size_t ring_smem_bytes(const ImageHeader &h) { return (size_t)h.blob_bytes + (size_t)RING_CAP * LANE_THREADS * 2 + 16; }
-
+// exact duplicate check of a candidate against this step's new ring entries
 __device__ __noinline__ bool ring_contains(const uint8_t *lb, uint32_t from, uint32_t to, uint32_t row, uint32_t rmask, uint32_t t) {
     for (uint32_t o = from; o != to; o = (o + row) & rmask)
         if (*reinterpret_cast<const uint16_t *>(lb + o) == t) return true;
@@ -403,7 +85,7 @@ __device__ __noinline__ bool ring_contains(const uint8_t *lb, uint32_t from, uin
 
 template <int W>
 __global__ void __launch_bounds__(LANE_THREADS, 1)
-scan_lane_ring_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
+scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     extern __shared__ __align__(128) uint8_t smem[];
     const ImageHeader &h = nfa.h;
     constexpr uint32_t ROW = LANE_THREADS * 2;          // bytes between consecutive ring entries of one lane
@@ -470,6 +152,7 @@ scan_lane_ring_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) 
             nextp += 16;
         }
 
+        // add target t to S_{k+1}: sticky targets set a mask bit, the others join the ring unless already there
         auto push = [&](uint32_t t) {
             if (t < nsb) {
                 const uint64_t sb = 1ull << (t & 63);
@@ -478,9 +161,9 @@ scan_lane_ring_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) 
             }
             const uint32_t fb = 1u << (t & 31);
             const bool fh = (t & 32) != 0;
-            if (((fh ? fhi : flo) & fb) && ring_contains(lb, re, wp, ROW, RMASK, t)) return;
+            if (((fh ? fhi : flo) & fb) && ring_contains(lb, re, wp, ROW, RMASK, t)) return;   // filter hit: exact check (rare)
             const uint32_t nw = (wp + ROW) & RMASK;
-            if (nw == rp) { ovf = true; return; }
+            if (nw == rp) { ovf = true; return; }                 // ring full: hand the stream to the general kernel
             *reinterpret_cast<uint16_t *>(lb + wp) = (uint16_t)t;
             wp = nw;
             if (fh) fhi |= fb; else flo |= fb;
@@ -597,22 +280,11 @@ scan_lane_ring_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) 
 }
 
 cudaError_t launch_scan_lane(const NfaDev &nfa, const BatchDev &batch, const OutDev &out, int n_sms, cudaStream_t stream) {
-    static const bool use_ring = [] { const char *m = getenv("RFB_LANE_MODE"); return m && m[0] == 'r'; }();
-    if (use_ring) {
-        const size_t smem = ring_smem_bytes(nfa.h);
-        unsigned long long want = (batch.n_streams + LANE_THREADS - 1) / LANE_THREADS;
-        int grid = (int)(want < (unsigned long long)n_sms ? (want ? want : 1) : (unsigned long long)n_sms);
-        if (nfa.h.sticky_words == 1) scan_lane_ring_kernel<1><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out);
-        else scan_lane_ring_kernel<2><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out);
-        return cudaGetLastError();
-    }
-    const uint32_t wcap = lane_wcap_for(nfa.h);
-    if (wcap < 64) return cudaErrorInvalidValue;
-    const size_t smem = lane_smem_bytes(nfa.h, wcap);
+    const size_t smem = lane_smem_bytes(nfa.h);
     unsigned long long want = (batch.n_streams + LANE_THREADS - 1) / LANE_THREADS;
     int grid = (int)(want < (unsigned long long)n_sms ? (want ? want : 1) : (unsigned long long)n_sms);
-    if (nfa.h.sticky_words == 1) scan_lane_kernel<1><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out, wcap);
-    else scan_lane_kernel<2><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out, wcap);
+    if (nfa.h.sticky_words == 1) scan_lane_kernel<1><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out);
+    else scan_lane_kernel<2><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out);
     return cudaGetLastError();
 }
 
@@ -749,8 +421,6 @@ cudaError_t configure_kernels() {
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(scan_lane_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(scan_lane_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(scan_lane_ring_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(scan_lane_ring_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(scan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM);
 }
 
