@@ -15,9 +15,12 @@ struct rfb_ctx {
     int device = 0;
     int n_sms = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;     // rfb_scan: H2D of chunk i+1 overlaps the kernels of chunk i
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_chunk[16] = {};          // chunk i resident
     ScanGlobals *g = nullptr;          // device
     ScanGlobals *g_host = nullptr;     // pinned
+    unsigned int *chunk_vals = nullptr; // pinned {1..16}: sources of the chunks_ready updates
     uint2 *rescan = nullptr;
     size_t rescan_cap = 0;
     // grow-only staging for rfb_scan (host-pointer variant)
@@ -123,15 +126,20 @@ int rfb_ctx_create(int device_id, rfb_ctx **out) {
                                                  std::to_string(prop.minor) + "; this library is built for sm_100a only");
     }
     ctx->n_sms = prop.multiProcessorCount;
+    for (int i = 0; i < 16; i++)
+        if ((e = cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming)) != cudaSuccess) { int rc = cuda_fail(nullptr, e, "event"); rfb_ctx_destroy(ctx); return rc; }
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&ctx->g), sizeof(ScanGlobals))) != cudaSuccess ||
         (e = cudaMallocHost(reinterpret_cast<void **>(&ctx->g_host), sizeof(ScanGlobals))) != cudaSuccess ||
+        (e = cudaMallocHost(reinterpret_cast<void **>(&ctx->chunk_vals), 16 * sizeof(unsigned int))) != cudaSuccess ||
         (e = configure_kernels()) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "context setup");
         rfb_ctx_destroy(ctx);
         return rc;
     }
+    for (unsigned i = 0; i < 16; i++) ctx->chunk_vals[i] = i + 1;
     *out = ctx;
     return RFB_OK;
 }
@@ -140,10 +148,13 @@ void rfb_ctx_destroy(rfb_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+    for (int i = 0; i < 16; i++) if (ctx->ev_chunk[i]) cudaEventDestroy(ctx->ev_chunk[i]);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     cudaFree(ctx->g);
     if (ctx->g_host) cudaFreeHost(ctx->g_host);
+    if (ctx->chunk_vals) cudaFreeHost(ctx->chunk_vals);
     cudaFree(ctx->rescan);
     cudaFree(ctx->d_data); cudaFree(ctx->d_offsets); cudaFree(ctx->d_steps);
     cudaFree(ctx->d_counts); cudaFree(ctx->d_records);
@@ -311,11 +322,35 @@ int rfb_scan_collect(rfb_ctx *ctx, rfb_result *res) {
     res->n_records = res->records ? std::min<uint64_t>(g.n_matches, res->record_capacity) : 0;
     res->n_dropped = g.n_matches - res->n_records;
     res->n_symbols = ctx->last_ragged ? g.n_symbols : ctx->last_symbols;
-    res->n_rescanned = g.n_rescan;
+    res->n_rescanned = g.n_rescan_total;
     res->n_launches = ctx->last_launches;
     float ms = 0.f;
     CU(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     res->gpu_ms = ms;
+    return RFB_OK;
+}
+
+// Enqueues the scan kernels of one batch (device pointers) on `st`.  The globals must already be reset.
+static int enqueue_kernels(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flags, const rfb_result *res,
+                           cudaStream_t st, uint32_t *launches, unsigned int chunk_streams = 0) {
+    BatchDev bd;
+    bd.data = b->data; bd.n_streams = b->n_streams; bd.stride = b->stride;
+    bd.offsets = reinterpret_cast<const unsigned long long *>(b->offsets);
+    bd.steps = b->steps; bd.n_steps = b->n_steps; bd.stream_id_base = b->stream_id_base;
+    bd.chunk_streams = chunk_streams; bd.ready = &ctx->g->chunks_ready;
+    OutDev od;
+    od.counts = (flags & RFB_SCAN_NO_COUNTS) ? nullptr : reinterpret_cast<unsigned long long *>(res->counts);
+    od.records = res->records; od.capacity = res->records ? res->record_capacity : 0;
+    od.g = ctx->g; od.rescan = ctx->rescan;
+    if (b->n_streams) {
+        const bool lane = nfa->img.ok && !(flags & RFB_SCAN_FORCE_WARP);
+        if (lane) {
+            CU(ctx, launch_scan_lane(nfa->dev, bd, od, ctx->n_sms, st)); (*launches)++;
+            CU(ctx, launch_scan_warp(nfa->dev, bd, od, true, ctx->n_sms, st)); (*launches)++;
+        } else {
+            CU(ctx, launch_scan_warp(nfa->dev, bd, od, false, ctx->n_sms, st)); (*launches)++;
+        }
+    }
     return RFB_OK;
 }
 
@@ -330,32 +365,16 @@ int rfb_scan_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
     if (ctx->rescan_cap < b->n_streams) CU(ctx, ensure(ctx->rescan, ctx->rescan_cap, (size_t)b->n_streams));
 
     if (flags & RFB_SCAN_ACCUMULATE) {
-        CU(ctx, cudaMemsetAsync(&ctx->g->next_stream, 0, 4 * sizeof(unsigned int), st));
+        CU(ctx, cudaMemsetAsync(&ctx->g->next_stream, 0, 3 * sizeof(unsigned int), st));
     } else {
         CU(ctx, cudaMemsetAsync(ctx->g, 0, sizeof(ScanGlobals), st));
         if (res->counts && !(flags & RFB_SCAN_NO_COUNTS))
             CU(ctx, cudaMemsetAsync(res->counts, 0, (size_t)nfa->host.n_states * sizeof(uint64_t), st));
     }
-    BatchDev bd;
-    bd.data = b->data; bd.n_streams = b->n_streams; bd.stride = b->stride;
-    bd.offsets = reinterpret_cast<const unsigned long long *>(b->offsets);
-    bd.steps = b->steps; bd.n_steps = b->n_steps; bd.stream_id_base = b->stream_id_base;
-    OutDev od;
-    od.counts = (flags & RFB_SCAN_NO_COUNTS) ? nullptr : reinterpret_cast<unsigned long long *>(res->counts);
-    od.records = res->records; od.capacity = res->records ? res->record_capacity : 0;
-    od.g = ctx->g; od.rescan = ctx->rescan;
-
     uint32_t launches = 0;
     CU(ctx, cudaEventRecord(ctx->ev0, st));
-    if (b->n_streams) {
-        const bool lane = nfa->img.ok && !(flags & RFB_SCAN_FORCE_WARP);
-        if (lane) {
-            CU(ctx, launch_scan_lane(nfa->dev, bd, od, ctx->n_sms, st)); launches++;
-            CU(ctx, launch_scan_warp(nfa->dev, bd, od, true, ctx->n_sms, st)); launches++;
-        } else {
-            CU(ctx, launch_scan_warp(nfa->dev, bd, od, false, ctx->n_sms, st)); launches++;
-        }
-    }
+    rc = enqueue_kernels(ctx, nfa, b, flags, res, st, &launches);
+    if (rc) return rc;
     CU(ctx, cudaEventRecord(ctx->ev1, st));
     ctx->last_stream = st;
     ctx->last_ragged = b->steps != nullptr;
@@ -367,13 +386,14 @@ int rfb_scan_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
 
 int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flags, rfb_result *res) {
     if (!ctx || !nfa || !res) return fail(ctx, RFB_E_INVALID, "NULL argument");
+    if (nfa->ctx != ctx) return fail(ctx, RFB_E_INVALID, "nfa belongs to another context");
     int rc = check_batch(ctx, b, true);
     if (rc) return rc;
     cudaSetDevice(ctx->device);
-    cudaStream_t st = ctx->stream;
+    cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
     const size_t padded = ((size_t)b->data_bytes + 15) / 16 * 16 + 16;
     CU(ctx, ensure(ctx->d_data, ctx->d_data_cap, padded));
-    if (b->data_bytes) CU(ctx, cudaMemcpyAsync(ctx->d_data, b->data, b->data_bytes, cudaMemcpyHostToDevice, st));
+    if (ctx->rescan_cap < b->n_streams) CU(ctx, ensure(ctx->rescan, ctx->rescan_cap, (size_t)b->n_streams));
     rfb_batch db = *b;
     db.data = ctx->d_data;
     if (b->offsets) {
@@ -391,12 +411,54 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     if (want_counts) {
         CU(ctx, ensure(ctx->d_counts, ctx->d_counts_cap, (size_t)nfa->host.n_states));
         dr.counts = reinterpret_cast<uint64_t *>(ctx->d_counts);
+        CU(ctx, cudaMemsetAsync(ctx->d_counts, 0, (size_t)nfa->host.n_states * 8, st));
     } else dr.counts = nullptr;
     if (res->records && res->record_capacity) {
         CU(ctx, ensure(ctx->d_records, ctx->d_records_cap, (size_t)res->record_capacity));
         dr.records = ctx->d_records;
     } else { dr.records = nullptr; dr.record_capacity = 0; }
-    rc = rfb_scan_device(ctx, nfa, &db, flags & ~(RFB_SCAN_SORT_RECORDS | RFB_SCAN_ASYNC | RFB_SCAN_ACCUMULATE), st, &dr);
+    const uint32_t kflags = flags & (RFB_SCAN_FORCE_WARP | RFB_SCAN_NO_COUNTS);
+    CU(ctx, cudaMemsetAsync(ctx->g, 0, sizeof(ScanGlobals), st));
+
+    // Uniformly strided batches are copied in up to 16 chunks of whole streams on the copy stream; after each
+    // chunk the copy stream bumps g->chunks_ready.  ONE lane-kernel launch over the whole batch runs beside the
+    // copies: its warps take streams in ascending order and wait for their chunk's counter, so the kernel
+    // overlaps the H2D transfer at full occupancy.  Other batches (explicit offsets, general kernel only) wait
+    // for the whole copy.
+    uint32_t launches = 0;
+    const bool lane_path = nfa->img.ok && !(flags & RFB_SCAN_FORCE_WARP);
+    uint64_t n_chunks = 1;
+    if (lane_path && !b->offsets && b->n_streams >= 64 && b->stride > 0)
+        n_chunks = std::min<uint64_t>(16, std::max<uint64_t>(1, b->data_bytes / (64ull << 20)));
+    const uint64_t chunk_streams = n_chunks > 1 ? ((b->n_streams + n_chunks - 1) / n_chunks + 31) / 32 * 32 : 0;
+    CU(ctx, cudaEventRecord(ctx->ev_chunk[0], st));                  // globals reset before the first flag write
+    CU(ctx, cudaStreamWaitEvent(cs, ctx->ev_chunk[0], 0));
+    CU(ctx, cudaEventRecord(ctx->ev0, st));
+    if (n_chunks > 1) {
+        // copies first: with pageable host memory they complete before the launch below (no overlap, no hazard)
+        for (uint64_t c = 0; c < n_chunks; c++) {
+            const uint64_t s0 = std::min<uint64_t>(c * chunk_streams, b->n_streams);
+            const uint64_t s1 = std::min<uint64_t>((c + 1) * chunk_streams, b->n_streams);
+            const size_t lo = (size_t)(s0 * b->stride);
+            const size_t hi = (c + 1 == n_chunks || s1 == b->n_streams) ? (size_t)b->data_bytes : (size_t)(s1 * b->stride);
+            if (hi > lo) CU(ctx, cudaMemcpyAsync(ctx->d_data + lo, b->data + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+            CU(ctx, cudaMemcpyAsync(&ctx->g->chunks_ready, &ctx->chunk_vals[c], sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
+        }
+        rc = enqueue_kernels(ctx, nfa, &db, kflags, &dr, st, &launches, (unsigned int)chunk_streams);
+        if (rc) return rc;
+    } else {
+        if (b->data_bytes) CU(ctx, cudaMemcpyAsync(ctx->d_data, b->data, b->data_bytes, cudaMemcpyHostToDevice, cs));
+        CU(ctx, cudaEventRecord(ctx->ev_chunk[1], cs));
+        CU(ctx, cudaStreamWaitEvent(st, ctx->ev_chunk[1], 0));
+        rc = enqueue_kernels(ctx, nfa, &db, kflags, &dr, st, &launches);
+        if (rc) return rc;
+    }
+    CU(ctx, cudaEventRecord(ctx->ev1, st));
+    ctx->last_stream = st;
+    ctx->last_ragged = b->steps != nullptr;
+    ctx->last_symbols = b->steps ? 0 : b->n_streams * (unsigned long long)b->n_steps;
+    ctx->last_launches = launches;
+    rc = rfb_scan_collect(ctx, &dr);
     if (rc) return rc;
     if (want_counts) CU(ctx, cudaMemcpyAsync(res->counts, ctx->d_counts, (size_t)nfa->host.n_states * 8, cudaMemcpyDeviceToHost, st));
     if (dr.n_records) CU(ctx, cudaMemcpyAsync(res->records, ctx->d_records, dr.n_records * sizeof(rfb_match), cudaMemcpyDeviceToHost, st));

@@ -13,7 +13,9 @@ struct ScanGlobals {
     unsigned int next_stream;       // lane kernel: dynamic stream fetch
     unsigned int n_rescan;          // streams queued for the warp kernel
     unsigned int next_item;         // warp kernel: dynamic work fetch
-    unsigned int pad;
+    unsigned int n_rescan_total;    // handed-over streams (accumulates when the three above are reset between launches)
+    unsigned int chunks_ready;      // rfb_scan: input chunks whose H2D copy has completed (written by the copy stream)
+    unsigned int pad[3];
 };
 
 struct BatchDev {
@@ -24,6 +26,9 @@ struct BatchDev {
     const unsigned int *steps;          // nullable
     unsigned int n_steps;
     unsigned int stream_id_base;
+    // rfb_scan only: streams [c*chunk_streams, (c+1)*chunk_streams) become readable when *ready > c (0: no gating)
+    unsigned int chunk_streams;
+    const unsigned int *ready;
 };
 
 struct OutDev {

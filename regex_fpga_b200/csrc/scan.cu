@@ -116,6 +116,13 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
         if (lane == 0) base = atomicAdd(&out.g->next_stream, 32u);
         base = __shfl_sync(FULL, base, 0);
         if (base >= batch.n_streams) break;
+        if (batch.chunk_streams) {   // host path: wait until the H2D copy of this warp's chunk has landed
+            if (lane == 0) {
+                const unsigned int need = min(base + 31u, (unsigned int)batch.n_streams - 1u) / batch.chunk_streams + 1u;
+                while (*reinterpret_cast<const volatile unsigned int *>(batch.ready) < need) __nanosleep(256);
+            }
+            __syncwarp();
+        }
         const uint32_t sid = base + lane;
         const bool valid = sid < batch.n_streams;
         const uint32_t nsteps = valid ? (batch.steps ? batch.steps[sid] : batch.n_steps) : 0u;
@@ -314,6 +321,7 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
 
     for (uint32_t w = lane; w < 2 * nw; w += 32) bits_cur[w] = 0;
     __syncwarp();
+    if (from_rescan && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&out.g->n_rescan_total, out.g->n_rescan);
 
     auto insert = [&](uint32_t t) {
         const uint32_t bit = 1u << (t & 31);

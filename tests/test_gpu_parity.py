@@ -204,6 +204,37 @@ def test_device_resident_scan_matches_host_scan(gpu_ctx, snort):
     assert got == recs_tuple(ref.records)
 
 
+def test_host_path_chunked_overlap_matches_device_path(gpu_ctx, snort):
+    """rfb_scan copies batches >= 128 MB in chunks on a second stream while ONE kernel launch consumes them
+    (warps wait on a per-chunk arrival counter).  Counts and records must equal the device-resident scan,
+    also with per-stream lengths and a non-default stream_id_base."""
+    import torch
+    nfa = gpu_ctx.nfa_from_entries(snort.entries)
+    n = 110000                                                        # 169 MB at stride 1536 -> 2 chunks; not a multiple of 32
+    dev = WL.make_batch_torch("wmix", snort.lo, snort.hi, n, "cuda:0", 1500, 1536)
+    host = dev.cpu().numpy()
+    counts = torch.zeros(snort.n_states, dtype=torch.int64, device="cuda:0")
+    cap = 1 << 19
+    recs = torch.zeros(cap * 3, dtype=torch.int32, device="cuda:0")
+    r = nfa.scan_device(dev.data_ptr(), dev.numel(), n, 1500, 1536, counts.data_ptr(), recs.data_ptr(), cap,
+                        cuda_stream=torch.cuda.current_stream().cuda_stream, stream_id_base=7)
+    want = sorted(map(tuple, recs.cpu().numpy().view(np.uint32).reshape(-1, 3)[: r.n_records].tolist()))
+    got = nfa.scan(host, n, n_steps=1500, stride=1536, record_capacity=cap, stream_id_base=7)
+    assert got.n_matches == r.n_matches and got.n_symbols == n * 1500
+    assert np.array_equal(got.counts, counts.cpu().numpy().astype(np.uint64))
+    assert recs_tuple(got.records) == want
+    steps = np.full(n, 1500, np.uint32)
+    steps[::5] = 700
+    steps[3::7] = 0
+    ragged = nfa.scan(host, n, stride=1536, steps=steps, record_capacity=cap)
+    sub = np.arange(0, n, 997)
+    for s in sub[:60]:
+        b = O.b_scan(snort.entries, snort.n_states, host[s], int(steps[s]), stream_id=int(s))
+        mine = ragged.records[ragged.records["stream"] == s]
+        assert recs_tuple(mine) == recs_tuple(b["recs"])
+    assert ragged.n_symbols == int(steps.sum())
+
+
 def test_large_batch_properties(gpu_ctx, snort):
     """Full-size-shaped batch (256K streams here; bench runs 1M): size-independent properties --
     counts are additive over any partition of the streams, independent of stream order, and the lane
