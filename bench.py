@@ -108,6 +108,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 def cpu_sample(E, n_states, lo, hi, mix, n_pairs, first_stream=0):
     from regex_fpga_b200 import workloads as WL
+    if mix == "adv":
+        return WL.make_adversarial_numpy(E, n_states, hi, 2 * n_pairs, STREAM_LEN, STRIDE, seed=0x5EED0005 + first_stream)
     return WL.make_batch_numpy(mix, lo, hi, 2 * n_pairs, STREAM_LEN, STRIDE, SEED, first_stream)
 
 
@@ -211,7 +213,10 @@ def ours_arm(args, rank, world, local_rank):
     nfa = ctx.nfa_from_entries(E)
     n = args.streams
     first = rank * n
-    batch = WL.make_batch_torch(args.mix, lo, hi, n, dev, STREAM_LEN, STRIDE, SEED, first)
+    if args.mix == "adv":
+        batch = WL.make_adversarial_torch(E, n_states, hi, n, dev, STREAM_LEN, STRIDE, first_stream=first)
+    else:
+        batch = WL.make_batch_torch(args.mix, lo, hi, n, dev, STREAM_LEN, STRIDE, SEED, first)
     counts = torch.zeros(n_states, dtype=torch.int64, device=dev)
     cap = args.record_capacity
     recs = torch.empty(cap * 3, dtype=torch.int32, device=dev)
@@ -317,7 +322,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mix", default="wmix", choices=["wmix", "whi", "wlo", "uniform"])
+    ap.add_argument("--mix", default="wmix", choices=["wmix", "whi", "wlo", "uniform", "adv"])
     ap.add_argument("--streams", type=int, default=1 << 20, help="streams per GPU")
     ap.add_argument("--record-capacity", type=int, default=1 << 22)
     ap.add_argument("--e2e-steps", type=int, default=3)

@@ -56,6 +56,7 @@ constexpr int WARP_THREADS = 256;
 constexpr int WARP_LCAP = 512;       // sparse list entries per warp before it switches to bitmap scans
 
 size_t lane_smem_bytes(const ImageHeader &h);
+int lane_ring_cap(const ImageHeader &h);
 size_t warp_smem_bytes(uint32_t n_states, int warps_per_cta);
 
 // Enqueue the lane kernel (one thread per stream, tables in shared memory).

@@ -68,9 +68,14 @@ __device__ __forceinline__ void stage_image(uint8_t *dst, const uint8_t *src, ui
 // ------------------------------------------------------------------------------------------------
 // lane kernel
 // ------------------------------------------------------------------------------------------------
-constexpr int RING_CAP = 16;   // ring entries per stream (power of two)
-
-size_t lane_smem_bytes(const ImageHeader &h) { return (size_t)h.blob_bytes + (size_t)RING_CAP * LANE_THREADS * 2 + 16; }
+// ring entries per stream: the largest of 64 / 32 / 16 that fits beside the image (a full ring hands the stream
+// to the general kernel, which is an order of magnitude slower, so capacity is worth the shared memory)
+int lane_ring_cap(const ImageHeader &h) {
+    for (int cap = 64; cap >= 16; cap >>= 1)
+        if ((size_t)h.blob_bytes + (size_t)cap * LANE_THREADS * 2 + 16 <= MAX_DYN_SMEM) return cap;
+    return 0;
+}
+size_t lane_smem_bytes(const ImageHeader &h) { return (size_t)h.blob_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16; }
 
 // out-of-line copies for the lane kernel's hot loop (both are rare there)
 __device__ __noinline__ void emit_match_cold(const OutDev &out, uint32_t stream, uint32_t pos, uint32_t state) {
@@ -83,7 +88,7 @@ __device__ __noinline__ bool ring_contains(const uint8_t *lb, uint32_t from, uin
     return false;
 }
 
-template <int W>
+template <int W, int RING_CAP>
 __global__ void __launch_bounds__(LANE_THREADS, 1)
 scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -290,8 +295,14 @@ cudaError_t launch_scan_lane(const NfaDev &nfa, const BatchDev &batch, const Out
     const size_t smem = lane_smem_bytes(nfa.h);
     unsigned long long want = (batch.n_streams + LANE_THREADS - 1) / LANE_THREADS;
     int grid = (int)(want < (unsigned long long)n_sms ? (want ? want : 1) : (unsigned long long)n_sms);
-    if (nfa.h.sticky_words == 1) scan_lane_kernel<1><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out);
-    else scan_lane_kernel<2><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out);
+    const int cap = lane_ring_cap(nfa.h);
+    const bool w1 = nfa.h.sticky_words == 1;
+#define RFB_LAUNCH(W_, C_) scan_lane_kernel<W_, C_><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out)
+    if (cap == 64) { if (w1) RFB_LAUNCH(1, 64); else RFB_LAUNCH(2, 64); }
+    else if (cap == 32) { if (w1) RFB_LAUNCH(1, 32); else RFB_LAUNCH(2, 32); }
+    else if (cap == 16) { if (w1) RFB_LAUNCH(1, 16); else RFB_LAUNCH(2, 16); }
+    else return cudaErrorInvalidValue;
+#undef RFB_LAUNCH
     return cudaGetLastError();
 }
 
@@ -427,8 +438,9 @@ cudaError_t launch_scan_warp(const NfaDev &nfa, const BatchDev &batch, const Out
 
 cudaError_t configure_kernels() {
     cudaError_t e;
-    if ((e = cudaFuncSetAttribute(scan_lane_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(scan_lane_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM)) != cudaSuccess) return e;
+#define RFB_ATTR(W_, C_) if ((e = cudaFuncSetAttribute(scan_lane_kernel<W_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM)) != cudaSuccess) return e
+    RFB_ATTR(1, 16); RFB_ATTR(2, 16); RFB_ATTR(1, 32); RFB_ATTR(2, 32); RFB_ATTR(1, 64); RFB_ATTR(2, 64);
+#undef RFB_ATTR
     return cudaFuncSetAttribute(scan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM);
 }
 

@@ -88,3 +88,111 @@ def make_batch_torch(mix, lo, hi, n_streams, device, stream_len=1500, stride=153
         rows = torch.where(use_hi[:, None], wh[offs], wl[offs])
         out[s0:s0 + n, :stream_len] = rows
     return out
+
+
+# ---- BASELINE config 5: replicated large NFA and adversarial (high-activity) traces ---------------
+def decode_rows(entries, n_states):
+    """BRAM image -> (row_ptr, sym, tgt) numpy arrays (Design/FPGA.v:773,782,793,888-898)."""
+    e = np.asarray(entries, dtype=np.uint32)
+    rp = e[: n_states + 1].astype(np.int64)
+    tr = e[n_states + 1: n_states + 1 + int(rp[n_states])]
+    return rp, (tr >> np.uint32(24)).astype(np.int64), (tr & np.uint32(0xFFFFFF)).astype(np.int64)
+
+
+def encode_rows(rp, sym, tgt):
+    """(row_ptr, sym, tgt) -> BRAM image, zero-padded to whole 128-bit lines."""
+    tr = ((np.asarray(sym, dtype=np.uint64) << np.uint64(24)) | np.asarray(tgt, dtype=np.uint64)).astype(np.uint32)
+    e = np.concatenate([np.asarray(rp, dtype=np.uint32), tr])
+    pad = (-e.size) % 4
+    return np.concatenate([e, np.zeros(pad, np.uint32)])
+
+
+def replicate_nfa(entries, n_states, copies):
+    """`copies` disjoint replicas of an NFA behind ONE shared start state 0: replica r's state
+    s >= 1 becomes 1 + r*(n-1) + (s-1); state 0's row is the concatenation of every replica's state-0 row.
+    7 x snort_16 -> 66 592 states, 558 992 transitions (beyond the FPGA's own 16-bit rd_address)."""
+    rp, sym, tgt = decode_rows(entries, n_states)
+    n1 = n_states - 1
+    assert not np.any(tgt == 0), "nothing may target state 0"
+    rows_sym, rows_tgt, lens = [], [], []
+    s0 = slice(int(rp[0]), int(rp[1]))
+    rows_sym.append(np.concatenate([sym[s0]] * copies))
+    rows_tgt.append(np.concatenate([tgt[s0] + r * n1 for r in range(copies)]))
+    lens.append(rows_sym[0].size)
+    body = slice(int(rp[1]), int(rp[n_states]))
+    body_lens = np.diff(rp[1:])
+    for r in range(copies):
+        rows_sym.append(sym[body])
+        rows_tgt.append(tgt[body] + r * n1)
+        lens.extend(body_lens.tolist())
+    new_rp = np.concatenate([[0], np.cumsum(np.asarray(lens, dtype=np.int64))])
+    n_new = 1 + copies * n1
+    assert new_rp.size == n_new + 1
+    return encode_rows(new_rp, np.concatenate(rows_sym), np.concatenate(rows_tgt)), n_new
+
+
+def adversarial_prefixes(entries, n_states, avoid=(0x0A, 0x0D), min_self=254, root=1):
+    """Shortest symbol strings that drive the NFA from `root` (snort_16's global '.*' state) into each of its
+    long-lived self-looping states without using the bytes that kill the [^\\n\\r]* ones.  Feeding several of
+    them back to back accumulates persistent active states."""
+    rp, sym, tgt = decode_rows(entries, n_states)
+    avoid = set(avoid)
+    self_cnt = np.zeros(n_states, np.int64)
+    for s in range(n_states):
+        self_cnt[s] = int(np.sum(tgt[rp[s]:rp[s + 1]] == s))
+    goals = [s for s in range(n_states) if self_cnt[s] >= min_self and s != root]
+    def bfs(banned):
+        prev = {root: None}
+        frontier = [root]
+        while frontier:
+            nxt = []
+            for s in frontier:
+                for j in range(int(rp[s]), int(rp[s + 1])):
+                    t, c = int(tgt[j]), int(sym[j])
+                    if t not in prev and c not in banned:
+                        prev[t] = (s, c)
+                        nxt.append(t)
+            frontier = nxt
+        return prev
+    clean, anyb = bfs(avoid), bfs(set())   # prefer paths without the killer bytes, fall back to any path
+    out = []
+    for g in goals:
+        prev = clean if g in clean else anyb
+        if g not in prev:
+            continue
+        path, s = [], g
+        while prev[s] is not None:
+            s, c = prev[s]
+            path.append(c)
+        out.append(np.array(path[::-1], dtype=np.uint8))
+    return out
+
+
+def make_adversarial_numpy(entries, n_states, hi, n_streams, stream_len=1500, stride=1536, seed=0x5EED0005):
+    """Streams that start with a random concatenation of adversarial prefixes (about half of the stream) and
+    continue with a window of the hi trace."""
+    pref = adversarial_prefixes(entries, n_states)
+    rng = np.random.default_rng(seed)
+    hi = np.asarray(hi, dtype=np.uint8)
+    out = np.zeros((n_streams, stride), dtype=np.uint8)
+    for s in range(n_streams):
+        parts, total = [], 0
+        while total < stream_len // 2 and pref:
+            p = pref[int(rng.integers(len(pref)))]
+            parts.append(p)
+            total += p.size
+        head = np.concatenate(parts)[: stream_len // 2] if parts else np.zeros(0, np.uint8)
+        off = int(rng.integers(0, hi.size - stream_len))
+        body = hi[off: off + stream_len - head.size]
+        out[s, :stream_len] = np.concatenate([head, body])
+    return out
+
+
+def make_adversarial_torch(entries, n_states, hi, n_streams, device, stream_len=1500, stride=1536, seed=0x5EED0005,
+                           n_base=4096, first_stream=0):
+    """Device batch of adversarial streams: n_base distinct streams built on the host, then stream j is base
+    stream splitmix64(seed ^ j) mod n_base (a stress workload, not a throughput headline)."""
+    import torch
+    base = torch.from_numpy(make_adversarial_numpy(entries, n_states, hi, n_base, stream_len, stride, seed)).to(device)
+    pick = window_offsets(seed, first_stream, n_streams, n_base)
+    return base[torch.from_numpy(pick).to(device)].contiguous()

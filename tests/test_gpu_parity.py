@@ -204,6 +204,27 @@ def test_device_resident_scan_matches_host_scan(gpu_ctx, snort):
     assert got == recs_tuple(ref.records)
 
 
+def test_config5_replicated_large_nfa_adversarial(gpu_ctx, snort):
+    """BASELINE config 5: 7 x snort_16 behind one start state (66 592 states, beyond the FPGA's own 16-bit
+    rd_address) with adversarial high-activity streams and hi-trace windows.  Too large for the 15-bit ids of
+    the lane kernel's tables, so this exercises the general warp kernel on a big NFA; bit-exact vs oracle B."""
+    E7, n7 = WL.replicate_nfa(snort.entries, snort.n_states, 7)
+    assert n7 == 66592 and int(E7[n7]) == 558992
+    nfa = gpu_ctx.nfa_from_entries(E7, n7)
+    assert nfa.info["image_ok"] == 0
+    adv = WL.make_adversarial_numpy(snort.entries, snort.n_states, snort.hi, 96)
+    whi = WL.make_batch_numpy("whi", snort.lo, snort.hi, 96, 1500, 1536, seed=0x5EED0005)
+    data = np.concatenate([adv, whi])
+    got = check_against_oracle(nfa, E7, n7, data, 1500, R.SCAN_SORT_RECORDS)
+    assert got.n_matches > 100
+    # every replica sees the same bytes, so a match on state s of replica 0 appears on all 7 replicas
+    one = gpu_ctx.nfa_from_entries(snort.entries).scan(data, data.shape[0], n_steps=1500, stride=1536)
+    assert got.n_matches == 7 * one.n_matches
+    per = got.counts[1:].reshape(7, snort.n_states - 1)
+    assert all(np.array_equal(per[0], per[r]) for r in range(1, 7))
+    assert np.array_equal(per[0], one.counts[1:])
+
+
 def test_host_path_chunked_overlap_matches_device_path(gpu_ctx, snort):
     """rfb_scan copies batches >= 128 MB in chunks on a second stream while ONE kernel launch consumes them
     (warps wait on a per-chunk arrival counter).  Counts and records must equal the device-resident scan,

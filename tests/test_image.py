@@ -68,3 +68,21 @@ def test_too_large_for_shared_memory_falls_to_warp_kernel():
     E, n = build_entries(rows)
     info = R.image_check(E, n)
     assert info["image_ok"] == 0 and info["n_states"] == n
+
+
+def test_replicated_nfa_is_valid_but_too_large_for_the_lane_tables(snort):
+    """BASELINE config 5 image: 7 x snort_16 = 66 592 states; valid CSR, size auto-detectable, lane tables
+    not buildable (more than 32 768 slots) -> general kernel."""
+    from regex_fpga_b200 import workloads as WL
+    E7, n7 = WL.replicate_nfa(snort.entries, snort.n_states, 7)
+    assert n7 == 1 + 7 * 9513 and R.coe_detect_size(E7) == n7
+    info = R.image_check(E7, n7)
+    assert info["image_ok"] == 0 and info["n_accepting"] == 7 * 536 and info["n_transitions"] == 558992
+    E1, n1 = WL.replicate_nfa(snort.entries, snort.n_states, 1)
+    assert n1 == snort.n_states and np.array_equal(E1, snort.entries)
+
+
+def test_adversarial_prefixes_reach_long_lived_states(snort):
+    from regex_fpga_b200 import workloads as WL
+    pref = WL.adversarial_prefixes(snort.entries, snort.n_states)
+    assert len(pref) >= 40 and all(1 <= p.size < 200 for p in pref)
