@@ -39,6 +39,7 @@ struct rfb_ctx {
 
 struct rfb_nfa {
     rfb_ctx *ctx = nullptr;
+    int device = 0;                    // copy of ctx->device: the context may be destroyed first
     Nfa host;
     Image img;
     NfaDev dev{};
@@ -168,6 +169,7 @@ int rfb_nfa_from_entries(rfb_ctx *ctx, const uint32_t *entries, size_t n_entries
     rfb_nfa *nfa = new (std::nothrow) rfb_nfa();
     if (!nfa) return fail(ctx, RFB_E_NOMEM, "out of host memory");
     nfa->ctx = ctx;
+    nfa->device = ctx->device;
     std::string err;
     int rc = nfa_from_entries(entries, n_entries, n_states, nfa->host, err);
     if (rc) { delete nfa; return fail(ctx, rc, err); }
@@ -214,7 +216,7 @@ int rfb_nfa_load_coe(rfb_ctx *ctx, const char *path, int64_t n_states, rfb_nfa *
 
 void rfb_nfa_destroy(rfb_nfa *nfa) {
     if (!nfa) return;
-    if (nfa->ctx) cudaSetDevice(nfa->ctx->device);
+    cudaSetDevice(nfa->device);
     cudaFree(nfa->d_entries); cudaFree(nfa->d_blob); cudaFree(nfa->d_orig);
     delete nfa;
 }
@@ -361,6 +363,7 @@ int rfb_scan_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
     if (rc) return rc;
     if (flags & RFB_SCAN_SORT_RECORDS) return fail(ctx, RFB_E_UNSUPPORTED, "RFB_SCAN_SORT_RECORDS is only available through rfb_scan");
     cudaSetDevice(ctx->device);
+    (void)cudaGetLastError();   // a stale error of an unrelated earlier call must not be blamed on this launch
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
     if (ctx->rescan_cap < b->n_streams) CU(ctx, ensure(ctx->rescan, ctx->rescan_cap, (size_t)b->n_streams));
 
@@ -390,6 +393,7 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     int rc = check_batch(ctx, b, true);
     if (rc) return rc;
     cudaSetDevice(ctx->device);
+    (void)cudaGetLastError();
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
     const size_t padded = ((size_t)b->data_bytes + 15) / 16 * 16 + 16;
     CU(ctx, ensure(ctx->d_data, ctx->d_data_cap, padded));
@@ -476,8 +480,39 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     return RFB_OK;
 }
 
-int rfb_fpga_cycles(rfb_ctx *ctx, const rfb_nfa *, const uint8_t *, const uint8_t *, uint32_t, uint64_t *) {
-    return fail(ctx, RFB_E_UNSUPPORTED, "rfb_fpga_cycles is not implemented yet");
+int rfb_fpga_cycles(rfb_ctx *ctx, const rfb_nfa *nfa, const uint8_t *lo, const uint8_t *hi, uint32_t trace_entries, uint64_t *cycles) {
+    if (!ctx || !nfa || !lo || !hi || !cycles) return fail(ctx, RFB_E_INVALID, "NULL argument");
+    if (nfa->ctx != ctx) return fail(ctx, RFB_E_INVALID, "nfa belongs to another context");
+    if (trace_entries == 0) return fail(ctx, RFB_E_INVALID, "trace_entries must be >= 1");
+    cudaSetDevice(ctx->device);
+    (void)cudaGetLastError();
+    const Nfa &h = nfa->host;
+    // cost(s): cycles the FSM spends on an active state (Design/FPGA.v:158-743):
+    //   state 0 + state 1 + state 2 (two visits when s % 4 == 3: row_ptr[s+1] is on the next line, :187-205)
+    //   + state 3 (1 for an accepting state, else lines + 2 for the 3-deep line pipeline and its drain) + state 4
+    std::vector<uint32_t> cost(h.n_states);
+    const uint32_t *rp = h.row_ptr();
+    for (uint32_t s = 0; s < h.n_states; s++) {
+        const uint64_t deg = rp[s + 1] - rp[s];
+        const uint64_t s3 = deg == 0 ? 1 : ((((uint64_t)h.n_states + 1 + rp[s]) % 4 + deg + 3) / 4 + 2);
+        cost[s] = (uint32_t)(1 + 1 + ((s % 4 == 3) ? 2 : 1) + s3 + 1);
+    }
+    const uint32_t n_steps = trace_entries - 1;          // the last entry is loaded but never processed (TB:71-86)
+    uint32_t *d_cost = nullptr; uint8_t *d_tr = nullptr; unsigned long long *d_total = nullptr;
+    cudaError_t e;
+    int rc = RFB_OK;
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&d_cost), cost.size() * 4)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&d_tr), 2 * (size_t)trace_entries + 16)) != cudaSuccess ||
+        (e = cudaMalloc(reinterpret_cast<void **>(&d_total), 8)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_cost, cost.data(), cost.size() * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_tr, lo, trace_entries, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(d_tr + trace_entries, hi, trace_entries, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
+        (e = launch_tb_cycles(nfa->dev, d_cost, d_tr, d_tr + trace_entries, n_steps, d_total, ctx->stream)) != cudaSuccess ||
+        (e = cudaMemcpyAsync(cycles, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
+        (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
+        rc = cuda_fail(ctx, e, "rfb_fpga_cycles");
+    cudaFree(d_cost); cudaFree(d_tr); cudaFree(d_total);
+    return rc;
 }
 
 }  // extern "C"

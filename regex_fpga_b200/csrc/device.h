@@ -67,6 +67,8 @@ cudaError_t launch_scan_lane(const NfaDev &nfa, const BatchDev &batch, const Out
 //   lane kernel -- the count is read on the device, so no host round trip is needed in between.
 cudaError_t launch_scan_warp(const NfaDev &nfa, const BatchDev &batch, const OutDev &out, bool from_rescan,
                              int n_sms, cudaStream_t stream);
+cudaError_t launch_tb_cycles(const NfaDev &nfa, const uint32_t *cost, const uint8_t *lo, const uint8_t *hi, uint32_t n_steps,
+                             unsigned long long *total, cudaStream_t stream);
 cudaError_t configure_kernels();
 constexpr size_t MAX_DYN_SMEM = 227 * 1024;   // per-CTA opt-in limit on sm_100
 

@@ -436,11 +436,70 @@ cudaError_t launch_scan_warp(const NfaDev &nfa, const BatchDev &batch, const Out
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// testbench cycle model: "Total no. cycles" (testbench_BLK_Mem.sv:52,84) of the two-stream lock-step run
+// ------------------------------------------------------------------------------------------------
+// The FSM spends 1 cycle on every state index that is inactive in both streams (Design/FPGA.v:744-752) and
+// cost(s) cycles on every state active in either (FPGA.v:158-743; closed form in DESIGN.md section 9):
+//   step_cycles(k) = (size - |U_k|) + sum_{s in U_k} cost(s),  U_k = S_k(lo) | S_k(hi);  total = 1 + sum_k.
+// One CTA walks the pair: four bit vectors in shared memory, threads own bitmap words.
+__global__ void __launch_bounds__(256)
+tb_cycles_kernel(const NfaDev nfa, const uint32_t *__restrict__ cost, const uint8_t *__restrict__ lo,
+                 const uint8_t *__restrict__ hi, const uint32_t n_steps, unsigned long long *total) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t nw = (nfa.n_states + 31) / 32;
+    uint32_t *c1 = reinterpret_cast<uint32_t *>(smem), *c2 = c1 + nw, *n1 = c2 + nw, *n2 = n1 + nw;
+    unsigned long long &acc = *reinterpret_cast<unsigned long long *>(smem + (((size_t)4 * nw * 4 + 15) & ~(size_t)15));
+    const uint32_t *__restrict__ rp = nfa.row_ptr;
+    const uint32_t *__restrict__ tr = nfa.trans;
+    for (uint32_t w = threadIdx.x; w < 4 * nw; w += blockDim.x) c1[w] = 0;
+    if (threadIdx.x == 0) acc = 1;                       // the reset edge (testbench_BLK_Mem.sv:31-39)
+    __syncthreads();
+    if (threadIdx.x == 0) { c1[0] = 1; c2[0] = 1; }      // current[0] <= 1 for both streams (FPGA.v:146-147)
+    __syncthreads();
+    for (uint32_t k = 0; k < n_steps; k++) {
+        const uint32_t s1 = lo[k], s2 = hi[k];
+        unsigned long long mine = 0;
+        for (uint32_t w = threadIdx.x; w < nw; w += blockDim.x) {
+            const uint32_t a1 = c1[w], a2 = c2[w];
+            uint32_t u = a1 | a2;
+            const uint32_t valid = min(32u, nfa.n_states - w * 32);
+            mine += valid - __popc(u);
+            while (u) {
+                const uint32_t b = (uint32_t)__ffs((int)u) - 1u;
+                u &= u - 1;
+                const uint32_t s = w * 32 + b;
+                mine += cost[s];
+                const bool in1 = (a1 >> b) & 1u, in2 = (a2 >> b) & 1u;
+                for (uint32_t j = rp[s]; j < rp[s + 1]; j++) {
+                    const uint32_t e = tr[j], sy = e >> 24, t = e & 0xFFFFFFu;
+                    if (in1 && sy == s1) atomicOr(&n1[t >> 5], 1u << (t & 31));
+                    if (in2 && sy == s2) atomicOr(&n2[t >> 5], 1u << (t & 31));
+                }
+            }
+        }
+        if (mine) atomicAdd(&acc, mine);
+        __syncthreads();
+        for (uint32_t w = threadIdx.x; w < nw; w += blockDim.x) { c1[w] = n1[w]; c2[w] = n2[w]; n1[w] = 0; n2[w] = 0; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = acc;
+}
+
+cudaError_t launch_tb_cycles(const NfaDev &nfa, const uint32_t *cost, const uint8_t *lo, const uint8_t *hi, uint32_t n_steps,
+                             unsigned long long *total, cudaStream_t stream) {
+    const size_t smem = (((size_t)((nfa.n_states + 31) / 32) * 16 + 15) & ~(size_t)15) + 16;
+    if (smem > MAX_DYN_SMEM) return cudaErrorInvalidValue;
+    tb_cycles_kernel<<<1, 256, smem, stream>>>(nfa, cost, lo, hi, n_steps, total);
+    return cudaGetLastError();
+}
+
 cudaError_t configure_kernels() {
     cudaError_t e;
 #define RFB_ATTR(W_, C_) if ((e = cudaFuncSetAttribute(scan_lane_kernel<W_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM)) != cudaSuccess) return e
     RFB_ATTR(1, 16); RFB_ATTR(2, 16); RFB_ATTR(1, 32); RFB_ATTR(2, 32); RFB_ATTR(1, 64); RFB_ATTR(2, 64);
 #undef RFB_ATTR
+    if ((e = cudaFuncSetAttribute(tb_cycles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM)) != cudaSuccess) return e;
     return cudaFuncSetAttribute(scan_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM);
 }
 

@@ -6,6 +6,8 @@ state.  These classes expose exactly that through librfb200.so; all compute happ
 kernels -- there is no Python or CPU implementation of the scan anywhere in this package.
 """
 import ctypes as C
+import weakref
+
 import numpy as np
 
 from . import _lib
@@ -98,9 +100,12 @@ class Context:
         _check(self._L.rfb_ctx_create(device_id, C.byref(h)))
         self._h = h
         self.device_id = device_id
+        self._nfas = weakref.WeakSet()
 
     def close(self):
         if getattr(self, "_h", None):
+            for n in list(self._nfas):      # NFAs hold device memory of this context: release them first
+                n.close()
             self._L.rfb_ctx_destroy(self._h)
             self._h = None
 
@@ -149,6 +154,7 @@ class Nfa:
         self.ctx = ctx
         self._L = ctx._L
         self._h = handle
+        ctx._nfas.add(self)
         info = rfb_nfa_info()
         _check(self._L.rfb_nfa_get_info(self._h, C.byref(info)))
         self.info = _info_dict(info)
@@ -224,6 +230,16 @@ class Nfa:
             cuda_stream = 1
         _check(self._L.rfb_scan_device(self.ctx._h, self._h, C.byref(b), flags, cuda_stream, C.byref(r)), self.ctx._h)
         return r
+
+    def fpga_cycles(self, lo, hi, trace_entries):
+        """The testbench's "Total no. cycles" (testbench_BLK_Mem.sv:52,84) for an M-entry (lo, hi) trace pair."""
+        lo = np.ascontiguousarray(lo, dtype=np.uint8)
+        hi = np.ascontiguousarray(hi, dtype=np.uint8)
+        assert lo.size >= trace_entries and hi.size >= trace_entries
+        out = C.c_uint64()
+        _check(self._L.rfb_fpga_cycles(self.ctx._h, self._h, lo.ctypes.data_as(C.POINTER(C.c_uint8)),
+                                       hi.ctypes.data_as(C.POINTER(C.c_uint8)), trace_entries, C.byref(out)), self.ctx._h)
+        return int(out.value)
 
     def collect(self, r):
         _check(self._L.rfb_scan_collect(self.ctx._h, C.byref(r)), self.ctx._h)

@@ -204,6 +204,37 @@ def test_device_resident_scan_matches_host_scan(gpu_ctx, snort):
     assert got == recs_tuple(ref.records)
 
 
+@pytest.mark.parametrize("name", ["snort_16", "l7_filter"])
+def test_fpga_cycles_and_tb_report(gpu_ctx, snort, l7, expected, name, tmp_path):
+    """the testbench's printout from GPU results -- per-state counters of both streams and
+    `Total no. cycles` (closed-form cycle model of FPGA.v evaluated on the GPU) -- against the golden values the
+    cycle-level oracle produced (2 188 184 738 / 617 518 104 cycles)."""
+    from regex_fpga_b200 import tbreport
+    rs = snort if name == "snort_16" else l7
+    nfa = gpu_ctx.nfa_from_entries(rs.entries)
+    exp = expected["rulesets"][name]["tb"]
+    assert nfa.fpga_cycles(rs.lo, rs.hi, 2000) == exp["cycles_first_2000_entries"]
+    assert nfa.fpga_cycles(rs.lo, rs.hi, 1) == 1                      # reset edge only
+    lines, counters = tbreport.tb_report(nfa, rs.lo, rs.hi, expected["tb_trace_entries"])
+    assert lines[-1] == f"Total no. cycles: {exp['total_cycles']}"
+    for key, mc, label in (("lo", counters[0], "match_count"), ("hi", counters[1], "match_count_2")):
+        want = {int(s): c & 0x3FF for s, c in exp[key]["counts"].items()}
+        assert {int(p): int(mc[p]) for p in np.nonzero(mc)[0]} == want
+        mine = [ln for ln in lines if ln.startswith(label + "[")]
+        assert mine == [f"{label}[{p}] = {want[p]}" for p in sorted(want, reverse=True)]
+    # the CLI end to end, through the reference's own file formats
+    coe, lo, hi = tmp_path / "n.coe", tmp_path / "lo.mem", tmp_path / "hi.mem"
+    R.coe_write(coe, rs.entries, 1)
+    R.trace_write_mem(lo, rs.lo[:3000])
+    R.trace_write_mem(hi, rs.hi[:3000])
+    import io, contextlib
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        tbreport.main(["--coe", str(coe), "--lo", str(lo), "--hi", str(hi), "--entries", "3000"])
+    out = buf.getvalue().strip().split("\n")
+    assert out[-1] == f"Total no. cycles: {O.cycle_model(rs.entries, rs.n_states, rs.lo, rs.hi, 3000)}"
+
+
 def test_config5_replicated_large_nfa_adversarial(gpu_ctx, snort):
     """BASELINE config 5: 7 x snort_16 behind one start state (66 592 states, beyond the FPGA's own 16-bit
     rd_address) with adversarial high-activity streams and hi-trace windows.  Too large for the 15-bit ids of
