@@ -96,6 +96,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     constexpr uint32_t ROW = LANE_THREADS * 2;          // bytes between consecutive ring entries of one lane
     constexpr uint32_t RING = RING_CAP * ROW;
     constexpr uint32_t RMASK = RING - 1;
+    constexpr uint32_t NONE = 0xFFFFu;
     uint8_t *lists = smem + h.blob_bytes;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + h.blob_bytes + RING);
     stage_image(smem, nfa.blob, h.blob_bytes, bar);
@@ -107,135 +108,102 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     const uint16_t *cmap = reinterpret_cast<const uint16_t *>(smem + h.off_cmap);
     const uint16_t *t2 = reinterpret_cast<const uint16_t *>(smem + h.off_t2);
     const uint16_t *tl2 = reinterpret_cast<const uint16_t *>(smem + h.off_tl2);
-    uint8_t *lb = lists + threadIdx.x * 2;
+    uint8_t *lb = lists + threadIdx.x * 2;              // ring entry at byte offset o: *(uint16_t*)(lb + o); bank-conflict free
     const uint32_t gbase = h.gbase, nsb = h.nsb, hmul = h.hash_mul, hsh = h.hash_shift;
     const uint32_t nbm = (1u << h.bucket_bits) - 1u;
     const uint32_t acc_base = h.acc_base, n_acc = h.n_acc, nc2 = h.nc2;
     const bool accel = h.accel != 0;
     constexpr uint32_t MSTRIDE = 32u * W;
-    constexpr uint32_t FULL = 0xffffffffu;
-    const uint32_t lane = threadIdx.x & 31u;
+
+    // One THREAD per stream, and every thread walks its stream at its own pace: the loop below is flat.  An
+    // iteration either opens the next symbol step of the lane's stream (symbol fetch, two-symbol table, sticky
+    // masks) or drains ONE work item of the open step (a two-symbol-table hit, a member of the current set, a row
+    // of a firing sticky state) with one edge-table lookup and one insertion.  Lanes of a warp are at different
+    // symbols and different streams; a lane that finishes a stream takes the next one from a global counter, so
+    // busy and quiet streams balance automatically.
+    uint64_t P0 = 0, P1 = 0, Pn0 = 0, Pn1 = 0;          // sticky sets (P1/Pn1 unused when W == 1)
+    uint32_t rp = 0, re = 0, wp = 0;                    // ring byte offsets: next read, end of current set, next write
+    uint32_t flo = 0, fhi = 0;                          // 64-bit membership filter of this step's new entries
+    uint32_t pcls = 0;                                  // cls1 of the previous symbol if state A fired on it
+    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;            // remaining bytes of the current 16-byte chunk, next byte in b0[7:0]
+    uint4 pre = make_uint4(0, 0, 0, 0);                 // the chunk after it
+    uint32_t bufn = 0;
+    const uint8_t *nextp = nullptr, *endp = nullptr;
+    uint32_t sid = 0, k = 0, nsteps = 0;
+    uint32_t c = 0, hf = 0, hc = 0;                     // symbol of the open step and its hashes
+    uint32_t x = NONE;                                  // pending two-symbol-table value
+    uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;            // firing sticky bits not yet expanded
+    uint32_t idx = 0;
+    bool have = false, pend = false, walking = false, ovf = false;
 
     for (;;) {
-        unsigned int base = 0;
-        if (lane == 0) base = atomicAdd(&out.g->next_stream, 32u);
-        base = __shfl_sync(FULL, base, 0);
-        if (base >= batch.n_streams) break;
-        if (batch.chunk_streams) {   // host path: wait until the H2D copy of this warp's chunk has landed
-            if (lane == 0) {
-                const unsigned int need = min(base + 31u, (unsigned int)batch.n_streams - 1u) / batch.chunk_streams + 1u;
-                while (*reinterpret_cast<const volatile unsigned int *>(batch.ready) < need) __nanosleep(256);
+        if (!pend) {
+            if (have) {   // ---- close step k: current <= next (Design/FPGA.v:733-737) ----
+                P0 |= Pn0; Pn0 = 0;
+                if (W == 2) { P1 |= Pn1; Pn1 = 0; }
+                re = wp; flo = 0; fhi = 0;
+                k++;
+                if (ovf) {   // the ring filled up while S_{k} was being built: S_{k-1} was fully examined, the general
+                             // kernel re-runs the stream and reports from step k on
+                    if (k < nsteps) {
+                        const unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
+                        out.rescan[slot] = make_uint2(sid, k);
+                    }
+                    have = false; ovf = false;
+                } else if (k == nsteps) have = false;
             }
-            __syncwarp();
-        }
-        const uint32_t sid = base + lane;
-        const bool valid = sid < batch.n_streams;
-        const uint32_t nsteps = valid ? (batch.steps ? batch.steps[sid] : batch.n_steps) : 0u;
-        const uint32_t maxsteps = __reduce_max_sync(FULL, nsteps);
-
-        uint64_t P0 = 0, P1 = 0, Pn0 = 0, Pn1 = 0;
-        uint32_t rp = 0, re = 0, wp = 0;                // ring byte offsets: next read, end of current set, next write
-        uint32_t flo = 0, fhi = 0;                      // 64-bit membership filter of this step's new entries
-        uint32_t pcls = 0;
-        bool ovf = false;
-        uint32_t ovf_at = 0;
-        if (nsteps) {
-            if (h.start_id < nsb) {
-                if (W == 1 || h.start_id < 64) P0 = 1ull << (h.start_id & 63); else P1 = 1ull << (h.start_id & 63);
-            } else { *reinterpret_cast<uint16_t *>(lb) = (uint16_t)h.start_id; re = ROW; wp = ROW; }
-        }
-        uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;
-        uint4 pre = make_uint4(0, 0, 0, 0);
-        uint32_t bufn = 16;
-        const uint8_t *nextp = nullptr, *endp = nullptr;
-        if (nsteps) {
-            const uint8_t *sp = stream_ptr(batch, sid);
-            endp = sp + nsteps;
-            const uint8_t *b16 = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15);
-            const uint32_t off = (uint32_t)(sp - b16);
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(b16));
-            b0 = v.x; b1 = v.y; b2 = v.z; b3 = v.w;
-            for (uint32_t q = 0; q < off; q++) {
-                b0 = __funnelshift_r(b0, b1, 8); b1 = __funnelshift_r(b1, b2, 8); b2 = __funnelshift_r(b2, b3, 8); b3 >>= 8;
+            if (!have) {   // ---- next stream ----
+                for (;;) {
+                    sid = atomicAdd(&out.g->next_stream, 1u);
+                    if (sid >= batch.n_streams) break;
+                    nsteps = batch.steps ? batch.steps[sid] : batch.n_steps;
+                    if (nsteps) break;
+                }
+                if (sid >= batch.n_streams) break;      // this lane is done
+                if (batch.steps) atomicAdd(&out.g->n_symbols, (unsigned long long)nsteps);
+                if (batch.chunk_streams) {   // host path: wait until the H2D copy of this stream's chunk has landed
+                    const unsigned int need = sid / batch.chunk_streams + 1u;
+                    while (*reinterpret_cast<const volatile unsigned int *>(batch.ready) < need) __nanosleep(256);
+                }
+                P0 = 0; P1 = 0; Pn0 = 0; Pn1 = 0; rp = 0; re = 0; wp = 0; flo = 0; fhi = 0; pcls = 0; k = 0;
+                if (h.start_id < nsb) {                                               // Design/FPGA.v:146-147
+                    if (W == 1 || h.start_id < 64) P0 = 1ull << (h.start_id & 63); else P1 = 1ull << (h.start_id & 63);
+                } else { *reinterpret_cast<uint16_t *>(lb) = (uint16_t)h.start_id; re = ROW; wp = ROW; }
+                // input: aligned 16-byte chunks kept in registers, the first one shifted to the stream's first byte
+                const uint8_t *sp = stream_ptr(batch, sid);
+                endp = sp + nsteps;
+                const uint8_t *b16 = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15);
+                const uint32_t off = (uint32_t)(sp - b16);
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(b16));
+                b0 = v.x; b1 = v.y; b2 = v.z; b3 = v.w;
+                for (uint32_t q = 0; q < off; q++) {    // once per stream; off == 0 for aligned batches
+                    b0 = __funnelshift_r(b0, b1, 8); b1 = __funnelshift_r(b1, b2, 8); b2 = __funnelshift_r(b2, b3, 8); b3 >>= 8;
+                }
+                bufn = 16 - off;
+                nextp = b16 + 16;
+                if (nextp < endp) pre = __ldg(reinterpret_cast<const uint4 *>(nextp));
+                nextp += 16;
+                have = true;
             }
-            bufn = 16 - off;
-            nextp = b16 + 16;
-            if (nextp < endp) pre = __ldg(reinterpret_cast<const uint4 *>(nextp));
-            nextp += 16;
-        }
-
-        // add target t to S_{k+1}: sticky targets set a mask bit, the others join the ring unless already there
-        auto push = [&](uint32_t t) {
-            if (t < nsb) {
-                const uint64_t sb = 1ull << (t & 63);
-                if (W == 1 || t < 64) Pn0 |= sb; else Pn1 |= sb;
-                return;
-            }
-            const uint32_t fb = 1u << (t & 31);
-            const bool fh = (t & 32) != 0;
-            if (((fh ? fhi : flo) & fb) && ring_contains(lb, re, wp, ROW, RMASK, t)) return;   // filter hit: exact check (rare)
-            const uint32_t nw = (wp + ROW) & RMASK;
-            if (nw == rp) { ovf = true; return; }                 // ring full: hand the stream to the general kernel
-            *reinterpret_cast<uint16_t *>(lb + wp) = (uint16_t)t;
-            wp = nw;
-            if (fh) fhi |= fb; else flo |= fb;
-        };
-        auto lookup = [&](uint32_t &idx, bool &walking, uint32_t c) {
-            const uint32_t e = tab[idx];
-            const uint32_t a = e & 0xFFu, b = (e >> 8) & 0xFFu, t = (e >> 16) & 0x7FFFu;
-            bool hit;
-            walking = (e & TAB_MORE) != 0;
-            idx++;
-            if (a <= b) hit = (c == a) | (c == b);
-            else if (a == 0xFFu) { hit = false; idx = t; walking = true; }
-            else hit = (memb[((0xFEu - a) * 253u + b) * 8 + (c >> 5)] >> (c & 31)) & 1u;
-            if (hit && !ovf) push(t);
-        };
-
-        for (uint32_t k = 0; k < maxsteps; k++) {
-            const bool act = k < nsteps && !ovf;
+            // ---- open step k: next symbol ----
             if (bufn == 0) {
                 b0 = pre.x; b1 = pre.y; b2 = pre.z; b3 = pre.w; bufn = 16;
                 if (nextp < endp) pre = __ldg(reinterpret_cast<const uint4 *>(nextp));
                 nextp += 16;
             }
-            const uint32_t c = b0 & 0xFFu;
+            c = b0 & 0xFFu;
             b0 = __funnelshift_r(b0, b1, 8); b1 = __funnelshift_r(b1, b2, 8); b2 = __funnelshift_r(b2, b3, 8); b3 >>= 8;
             bufn--;
-            const uint32_t hf = ((c * hmul) >> hsh) & 0xFFu;
-            const uint32_t hc = hf & nbm;
-
+            hf = ((c * hmul) >> hsh) & 0xFFu;           // symbol hash; a row uses its low bits
+            hc = hf & nbm;
+            // two-symbol start table: successors of the never-materialised targets of state A
             if (accel) {
                 const uint32_t cm = cmap[c];
-                const uint32_t x = t2[pcls * nc2 + (cm >> 8)];
-                pcls = (act && (P0 & 1ull)) ? (cm & 0xFFu) : 0u;
-                if (act && x != 0xFFFFu) {
-                    if (x < 0x8000u) push(x);
-                    else { uint32_t q = x & 0x7FFFu, tl; do { tl = tl2[q++]; push(tl & 0x7FFFu); } while ((tl & 0x8000u) && !ovf); }
-                }
+                x = t2[pcls * nc2 + (cm >> 8)];
+                pcls = (P0 & 1ull) ? (cm & 0xFFu) : 0u;
             }
+            // sticky states: survivors P & K[c]; those in P & M[c] fire their rows
             {
-                bool walking = false;
-                uint32_t idx = 0;
-                bool work = act && rp != re;
-                while (__any_sync(FULL, work)) {
-                    if (work) {
-                        bool look = true;
-                        if (!walking) {
-                            const uint32_t u = *reinterpret_cast<const uint16_t *>(lb + rp);
-                            rp = (rp + ROW) & RMASK;
-                            idx = u + (u >= gbase ? hc : 0u);
-                            if (u - acc_base < n_acc) {
-                                emit_match_cold(out, sid + batch.stream_id_base, k, nfa.orig_of_id[u]);
-                                look = false;
-                            }
-                        }
-                        if (look) lookup(idx, walking, c);
-                        work = walking || rp != re;
-                    }
-                }
-            }
-            if (act) {
                 const uint8_t *mrow = mask + c * MSTRIDE;
                 bool attn;
                 if (W == 1) attn = (P0 & *reinterpret_cast<const uint64_t *>(mrow)) != 0;
@@ -244,7 +212,6 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     attn = (((uint32_t)P0 & a.x) | ((uint32_t)(P0 >> 32) & a.y) | ((uint32_t)P1 & a.z) | ((uint32_t)(P1 >> 32) & a.w)) != 0;
                 }
                 if (attn) {
-                    uint32_t i0, i1, i2 = 0, i3 = 0;
                     if (W == 1) {
                         const uint4 km = *reinterpret_cast<const uint4 *>(mrow + 16);
                         i0 = (uint32_t)P0 & km.z; i1 = (uint32_t)(P0 >> 32) & km.w;
@@ -257,36 +224,67 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                         P0 &= (uint64_t)kk.x | ((uint64_t)kk.y << 32);
                         P1 &= (uint64_t)kk.z | ((uint64_t)kk.w << 32);
                     }
-                    bool walking = false;
-                    uint32_t idx = 0;
-                    while (walking || (i0 | i1 | i2 | i3) != 0) {
-                        if (!walking) {
-                            uint32_t wsel, wbase;
-                            if (i0) { wsel = i0; wbase = 0; i0 &= i0 - 1; }
-                            else if (i1) { wsel = i1; wbase = 32; i1 &= i1 - 1; }
-                            else if (i2) { wsel = i2; wbase = 64; i2 &= i2 - 1; }
-                            else { wsel = i3; wbase = 96; i3 &= i3 - 1; }
-                            const uint32_t d = sdesc[wbase + (uint32_t)__ffs((int)wsel) - 1u];
-                            idx = (d & 0xFFFFu) + (hf & (d >> 16));
+                }
+            }
+            pend = x != NONE || rp != re || (i0 | i1 | i2 | i3) != 0;
+        }
+        if (pend) {   // ---- drain one work item of the open step ----
+            bool hit = false, look = walking;
+            uint32_t t = 0;
+            if (!walking) {
+                if (x != NONE) {                                  // two-symbol table hit: the target itself
+                    hit = true;
+                    if (x < 0x8000u) { t = x; x = NONE; }
+                    else { const uint32_t tl = tl2[x & 0x7FFFu]; t = tl & 0x7FFFu; x = (tl & 0x8000u) ? x + 1 : NONE; }
+                } else if (rp != re) {                            // a member of S_k
+                    const uint32_t u = *reinterpret_cast<const uint16_t *>(lb + rp);
+                    rp = (rp + ROW) & RMASK;
+                    idx = u + (u >= gbase ? hc : 0u);
+                    look = true;
+                    if (u - acc_base < n_acc) {                   // accepting (Design/FPGA.v:210-226)
+                        emit_match_cold(out, sid + batch.stream_id_base, k, nfa.orig_of_id[u]);
+                        look = false;
+                    }
+                } else {                                          // row of a firing sticky state
+                    uint32_t wsel, wbase;
+                    if (i0) { wsel = i0; wbase = 0; i0 &= i0 - 1; }
+                    else if (i1) { wsel = i1; wbase = 32; i1 &= i1 - 1; }
+                    else if (i2) { wsel = i2; wbase = 64; i2 &= i2 - 1; }
+                    else { wsel = i3; wbase = 96; i3 &= i3 - 1; }
+                    const uint32_t d = sdesc[wbase + (uint32_t)__ffs((int)wsel) - 1u];
+                    idx = (d & 0xFFFFu) + (hf & (d >> 16));
+                    look = true;
+                }
+            }
+            if (look) {
+                const uint32_t e = tab[idx];
+                const uint32_t a = e & 0xFFu, b = (e >> 8) & 0xFFu;
+                t = (e >> 16) & 0x7FFFu;
+                walking = (e & TAB_MORE) != 0;
+                idx++;
+                if (a <= b) hit = (c == a) | (c == b);
+                else if (a == 0xFFu) { idx = t; walking = true; }                     // indirect -> chain
+                else hit = (memb[((0xFEu - a) * 253u + b) * 8 + (c >> 5)] >> (c & 31)) & 1u;
+            }
+            if (hit && !ovf) {   // ---- the one insertion site: add t to S_{k+1} ----
+                if (t < nsb) {                                    // entering a sticky state
+                    const uint64_t sb = 1ull << (t & 63);
+                    if (W == 1 || t < 64) Pn0 |= sb; else Pn1 |= sb;
+                } else {
+                    const uint32_t fb = 1u << (t & 31);
+                    const bool fh = (t & 32) != 0;
+                    if (!(((fh ? fhi : flo) & fb) && ring_contains(lb, re, wp, ROW, RMASK, t))) {
+                        const uint32_t nw = (wp + ROW) & RMASK;
+                        if (nw == rp) ovf = true;                 // ring full: hand the stream to the general kernel
+                        else {
+                            *reinterpret_cast<uint16_t *>(lb + wp) = (uint16_t)t;
+                            wp = nw;
+                            if (fh) fhi |= fb; else flo |= fb;
                         }
-                        lookup(idx, walking, c);
                     }
                 }
-                P0 |= Pn0; Pn0 = 0;
-                if (W == 2) { P1 |= Pn1; Pn1 = 0; }
-                re = wp; flo = 0; fhi = 0;
-                if (ovf) ovf_at = k + 1;
             }
-        }
-        if (ovf && ovf_at < nsteps) {
-            const unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
-            out.rescan[slot] = make_uint2(sid, ovf_at);
-        }
-        if (batch.steps) {
-            unsigned long long tot = nsteps;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
-            if (lane == 0) atomicAdd(&out.g->n_symbols, tot);
+            pend = walking || x != NONE || rp != re || (i0 | i1 | i2 | i3) != 0;
         }
     }
 }
