@@ -97,6 +97,8 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     constexpr uint32_t RING = RING_CAP * ROW;
     constexpr uint32_t RMASK = RING - 1;
     constexpr uint32_t NONE = 0xFFFFu;
+    constexpr int DRAIN_REPS = 1;                       // work items a lane may drain per iteration (2 measured slower)
+    constexpr int OPEN_REPS = 1;                        // symbol steps a lane with nothing to drain may open per iteration (2 measured slower)
     uint8_t *lists = smem + h.blob_bytes;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + h.blob_bytes + RING);
     stage_image(smem, nfa.blob, h.blob_bytes, bar);
@@ -136,8 +138,10 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     uint32_t idx = 0;
     bool have = false, pend = false, walking = false, ovf = false;
 
+    bool done = false;
     for (;;) {
-        if (!pend) {
+#pragma unroll 1
+        for (int rep = 0; rep < OPEN_REPS && !pend; rep++) {
             if (have) {   // ---- close step k: current <= next (Design/FPGA.v:733-737) ----
                 P0 |= Pn0; Pn0 = 0;
                 if (W == 2) { P1 |= Pn1; Pn1 = 0; }
@@ -159,7 +163,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     nsteps = batch.steps ? batch.steps[sid] : batch.n_steps;
                     if (nsteps) break;
                 }
-                if (sid >= batch.n_streams) break;      // this lane is done
+                if (sid >= batch.n_streams) { done = true; break; }   // this lane is done
                 if (batch.steps) atomicAdd(&out.g->n_symbols, (unsigned long long)nsteps);
                 if (batch.chunk_streams) {   // host path: wait until the H2D copy of this stream's chunk has landed
                     const unsigned int need = sid / batch.chunk_streams + 1u;
@@ -228,7 +232,9 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             }
             pend = x != NONE || rp != re || (i0 | i1 | i2 | i3) != 0;
         }
-        if (pend) {   // ---- drain one work item of the open step ----
+        if (done) break;
+#pragma unroll 1
+        for (int rep = 0; rep < DRAIN_REPS && pend; rep++) {   // ---- drain work items of the open step ----
             bool hit = false, look = walking;
             uint32_t t = 0;
             if (!walking) {
