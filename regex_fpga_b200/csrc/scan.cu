@@ -77,14 +77,23 @@ int lane_ring_cap(const ImageHeader &h) {
 }
 size_t lane_smem_bytes(const ImageHeader &h) { return (size_t)h.blob_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16; }
 
+// explicit shared-window accesses: 32-bit shared addresses never go through generic-pointer conversion.
+// Table loads are plain asm (read-only data, the compiler may schedule them freely); ring accesses are volatile.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds16(uint32_t a) { uint16_t v; asm("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
+__device__ __forceinline__ uint2 lds64(uint32_t a) { uint2 v; asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t ring_ld(uint32_t a) { uint16_t v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void ring_st(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v) : "memory"); }
+
 // out-of-line copies for the lane kernel's hot loop (both are rare there)
 __device__ __noinline__ void emit_match_cold(const OutDev &out, uint32_t stream, uint32_t pos, uint32_t state) {
     emit_match(out, stream, pos, state);
 }
 // exact duplicate check of a candidate against this step's new ring entries
-__device__ __noinline__ bool ring_contains(const uint8_t *lb, uint32_t from, uint32_t to, uint32_t row, uint32_t rmask, uint32_t t) {
+__device__ __noinline__ bool ring_contains(uint32_t lb, uint32_t from, uint32_t to, uint32_t row, uint32_t rmask, uint32_t t) {
     for (uint32_t o = from; o != to; o = (o + row) & rmask)
-        if (*reinterpret_cast<const uint16_t *>(lb + o) == t) return true;
+        if (ring_ld(lb + o) == t) return true;
     return false;
 }
 
@@ -99,18 +108,14 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     constexpr uint32_t NONE = 0xFFFFu;
     constexpr int DRAIN_REPS = 1;                       // work items a lane may drain per iteration (2 measured slower)
     constexpr int OPEN_REPS = 1;                        // symbol steps a lane with nothing to drain may open per iteration (2 measured slower)
-    uint8_t *lists = smem + h.blob_bytes;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + h.blob_bytes + RING);
     stage_image(smem, nfa.blob, h.blob_bytes, bar);
 
-    const uint32_t *tab = reinterpret_cast<const uint32_t *>(smem + h.off_tab);
-    const uint8_t *mask = smem + h.off_mask;
-    const uint32_t *memb = reinterpret_cast<const uint32_t *>(smem + h.off_memb);
-    const uint32_t *sdesc = reinterpret_cast<const uint32_t *>(smem + h.off_sdesc);
-    const uint16_t *cmap = reinterpret_cast<const uint16_t *>(smem + h.off_cmap);
-    const uint16_t *t2 = reinterpret_cast<const uint16_t *>(smem + h.off_t2);
-    const uint16_t *tl2 = reinterpret_cast<const uint16_t *>(smem + h.off_tl2);
-    uint8_t *lb = lists + threadIdx.x * 2;              // ring entry at byte offset o: *(uint16_t*)(lb + o); bank-conflict free
+    // 32-bit shared-window addresses of the staged tables and of this lane's ring
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t tab_s = sbase + h.off_tab, mask_s = sbase + h.off_mask, memb_s = sbase + h.off_memb;
+    const uint32_t sdesc_s = sbase + h.off_sdesc, cmap_s = sbase + h.off_cmap, t2_s = sbase + h.off_t2, tl2_s = sbase + h.off_tl2;
+    const uint32_t lb = sbase + h.blob_bytes + threadIdx.x * 2;   // ring entry at byte offset o: lb + o; bank-conflict free
     const uint32_t gbase = h.gbase, nsb = h.nsb, hmul = h.hash_mul, hsh = h.hash_shift;
     const uint32_t nbm = (1u << h.bucket_bits) - 1u;
     const uint32_t acc_base = h.acc_base, n_acc = h.n_acc, nc2 = h.nc2;
@@ -172,7 +177,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                 P0 = 0; P1 = 0; Pn0 = 0; Pn1 = 0; rp = 0; re = 0; wp = 0; flo = 0; fhi = 0; pcls = 0; k = 0;
                 if (h.start_id < nsb) {                                               // Design/FPGA.v:146-147
                     if (W == 1 || h.start_id < 64) P0 = 1ull << (h.start_id & 63); else P1 = 1ull << (h.start_id & 63);
-                } else { *reinterpret_cast<uint16_t *>(lb) = (uint16_t)h.start_id; re = ROW; wp = ROW; }
+                } else { ring_st(lb, h.start_id); re = ROW; wp = ROW; }
                 // input: aligned 16-byte chunks kept in registers, the first one shifted to the stream's first byte
                 const uint8_t *sp = stream_ptr(batch, sid);
                 endp = sp + nsteps;
@@ -202,27 +207,27 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             hc = hf & nbm;
             // two-symbol start table: successors of the never-materialised targets of state A
             if (accel) {
-                const uint32_t cm = cmap[c];
-                x = t2[pcls * nc2 + (cm >> 8)];
+                const uint32_t cm = lds16(cmap_s + c * 2);
+                x = lds16(t2_s + (pcls * nc2 + (cm >> 8)) * 2);
                 pcls = (P0 & 1ull) ? (cm & 0xFFu) : 0u;
             }
             // sticky states: survivors P & K[c]; those in P & M[c] fire their rows
             {
-                const uint8_t *mrow = mask + c * MSTRIDE;
+                const uint32_t mrow = mask_s + c * MSTRIDE;
                 bool attn;
-                if (W == 1) attn = (P0 & *reinterpret_cast<const uint64_t *>(mrow)) != 0;
+                if (W == 1) { const uint2 a2 = lds64(mrow); attn = (((uint32_t)P0 & a2.x) | ((uint32_t)(P0 >> 32) & a2.y)) != 0; }
                 else {
-                    const uint4 a = *reinterpret_cast<const uint4 *>(mrow);
+                    const uint4 a = lds128(mrow);
                     attn = (((uint32_t)P0 & a.x) | ((uint32_t)(P0 >> 32) & a.y) | ((uint32_t)P1 & a.z) | ((uint32_t)(P1 >> 32) & a.w)) != 0;
                 }
                 if (attn) {
                     if (W == 1) {
-                        const uint4 km = *reinterpret_cast<const uint4 *>(mrow + 16);
+                        const uint4 km = lds128(mrow + 16);
                         i0 = (uint32_t)P0 & km.z; i1 = (uint32_t)(P0 >> 32) & km.w;
                         P0 &= (uint64_t)km.x | ((uint64_t)km.y << 32);
                     } else {
-                        const uint4 kk = *reinterpret_cast<const uint4 *>(mrow + 16);
-                        const uint4 mm = *reinterpret_cast<const uint4 *>(mrow + 32);
+                        const uint4 kk = lds128(mrow + 16);
+                        const uint4 mm = lds128(mrow + 32);
                         i0 = (uint32_t)P0 & mm.x; i1 = (uint32_t)(P0 >> 32) & mm.y;
                         i2 = (uint32_t)P1 & mm.z; i3 = (uint32_t)(P1 >> 32) & mm.w;
                         P0 &= (uint64_t)kk.x | ((uint64_t)kk.y << 32);
@@ -241,9 +246,9 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                 if (x != NONE) {                                  // two-symbol table hit: the target itself
                     hit = true;
                     if (x < 0x8000u) { t = x; x = NONE; }
-                    else { const uint32_t tl = tl2[x & 0x7FFFu]; t = tl & 0x7FFFu; x = (tl & 0x8000u) ? x + 1 : NONE; }
+                    else { const uint32_t tl = lds16(tl2_s + (x & 0x7FFFu) * 2); t = tl & 0x7FFFu; x = (tl & 0x8000u) ? x + 1 : NONE; }
                 } else if (rp != re) {                            // a member of S_k
-                    const uint32_t u = *reinterpret_cast<const uint16_t *>(lb + rp);
+                    const uint32_t u = ring_ld(lb + rp);
                     rp = (rp + ROW) & RMASK;
                     idx = u + (u >= gbase ? hc : 0u);
                     look = true;
@@ -257,20 +262,20 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     else if (i1) { wsel = i1; wbase = 32; i1 &= i1 - 1; }
                     else if (i2) { wsel = i2; wbase = 64; i2 &= i2 - 1; }
                     else { wsel = i3; wbase = 96; i3 &= i3 - 1; }
-                    const uint32_t d = sdesc[wbase + (uint32_t)__ffs((int)wsel) - 1u];
+                    const uint32_t d = lds32(sdesc_s + (wbase + (uint32_t)__ffs((int)wsel) - 1u) * 4);
                     idx = (d & 0xFFFFu) + (hf & (d >> 16));
                     look = true;
                 }
             }
             if (look) {
-                const uint32_t e = tab[idx];
+                const uint32_t e = lds32(tab_s + idx * 4);
                 const uint32_t a = e & 0xFFu, b = (e >> 8) & 0xFFu;
                 t = (e >> 16) & 0x7FFFu;
                 walking = (e & TAB_MORE) != 0;
                 idx++;
                 if (a <= b) hit = (c == a) | (c == b);
                 else if (a == 0xFFu) { idx = t; walking = true; }                     // indirect -> chain
-                else hit = (memb[((0xFEu - a) * 253u + b) * 8 + (c >> 5)] >> (c & 31)) & 1u;
+                else hit = (lds32(memb_s + (((0xFEu - a) * 253u + b) * 8 + (c >> 5)) * 4) >> (c & 31)) & 1u;
             }
             if (hit && !ovf) {   // ---- the one insertion site: add t to S_{k+1} ----
                 if (t < nsb) {                                    // entering a sticky state
@@ -283,7 +288,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                         const uint32_t nw = (wp + ROW) & RMASK;
                         if (nw == rp) ovf = true;                 // ring full: hand the stream to the general kernel
                         else {
-                            *reinterpret_cast<uint16_t *>(lb + wp) = (uint16_t)t;
+                            ring_st(lb + wp, t);
                             wp = nw;
                             if (fh) fhi |= fb; else flo |= fb;
                         }
