@@ -42,8 +42,10 @@ struct rfb_nfa {
     int device = 0;                    // copy of ctx->device: the context may be destroyed first
     Nfa host;
     Image img;
+    Ecsr ecsr;
     NfaDev dev{};
     uint32_t *d_entries = nullptr;
+    uint32_t *d_eptr = nullptr; unsigned long long *d_erec = nullptr; uint32_t *d_emembs = nullptr;
     uint8_t *d_blob = nullptr;
     uint32_t *d_orig = nullptr;
 };
@@ -176,6 +178,8 @@ int rfb_nfa_from_entries(rfb_ctx *ctx, const uint32_t *entries, size_t n_entries
     ImageOptions opt = default_image_options();
     rc = image_build(nfa->host, opt, nfa->img, err);
     if (rc) { delete nfa; return fail(ctx, rc, err); }
+    rc = ecsr_build(nfa->host, nfa->ecsr, err);
+    if (rc) { delete nfa; return fail(ctx, rc, err); }
 
     cudaSetDevice(ctx->device);
     const Nfa &h = nfa->host;
@@ -184,6 +188,19 @@ int rfb_nfa_from_entries(rfb_ctx *ctx, const uint32_t *entries, size_t n_entries
         (e = cudaMemcpy(nfa->d_entries, h.entries.data(), h.entries.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
         rfb_nfa_destroy(nfa);
         return cuda_fail(ctx, e, "upload CSR");
+    }
+    {
+        const Ecsr &ec = nfa->ecsr;
+        if ((e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_eptr), ec.eptr.size() * 4)) != cudaSuccess ||
+            (e = cudaMemcpy(nfa->d_eptr, ec.eptr.data(), ec.eptr.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_erec), std::max<size_t>(1, ec.erec.size()) * 8)) != cudaSuccess ||
+            (e = cudaMemcpy(nfa->d_erec, ec.erec.data(), ec.erec.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
+            (e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_emembs), ec.memb.size() * 4)) != cudaSuccess ||
+            (e = cudaMemcpy(nfa->d_emembs, ec.memb.data(), ec.memb.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            rfb_nfa_destroy(nfa);
+            return cuda_fail(ctx, e, "upload edge-grouped CSR");
+        }
+        nfa->dev.eptr = nfa->d_eptr; nfa->dev.erec = nfa->d_erec; nfa->dev.emembs = nfa->d_emembs;
     }
     nfa->dev.n_states = h.n_states;
     nfa->dev.row_ptr = nfa->d_entries;
@@ -218,6 +235,7 @@ void rfb_nfa_destroy(rfb_nfa *nfa) {
     if (!nfa) return;
     cudaSetDevice(nfa->device);
     cudaFree(nfa->d_entries); cudaFree(nfa->d_blob); cudaFree(nfa->d_orig);
+    cudaFree(nfa->d_eptr); cudaFree(nfa->d_erec); cudaFree(nfa->d_emembs);
     delete nfa;
 }
 
@@ -232,6 +250,7 @@ int rfb_image_check(const uint32_t *entries, size_t n_entries, int64_t n_states,
     if (!entries || !info) return fail(nullptr, RFB_E_INVALID, "NULL argument");
     Nfa host;
     Image img;
+    Ecsr ecsr;
     std::string err;
     int rc = nfa_from_entries(entries, n_entries, n_states, host, err);
     if (rc) return fail(nullptr, rc, err);

@@ -43,6 +43,10 @@ struct NfaDev {
     uint32_t n_states;
     const uint32_t *row_ptr;     // [n_states + 1]
     const uint32_t *trans;       // [nnz]  {symbol[31:24], target[23:0]}  Design/FPGA.v:888-898
+    // edge-grouped CSR (general kernel)
+    const uint32_t *eptr;        // [n_states + 1]
+    const unsigned long long *erec;   // [n_edges]
+    const uint32_t *emembs;      // [n_sets * 8]
     // execution image
     const uint8_t *blob;         // ImageHeader::blob_bytes bytes, 16-byte aligned
     const uint32_t *orig_of_id;  // [n_slots]

@@ -33,6 +33,20 @@ struct Nfa {
 // Validates and adopts an image.  n_states < 0: auto-detect.
 int nfa_from_entries(const uint32_t *entries, size_t n, int64_t n_states, Nfa &out, std::string &err);
 
+// ---- ecsr.cpp ---------------------------------------------------------------------------------
+// Edge-grouped CSR for the general kernel: a state's transitions grouped by target, one 64-bit record per
+// (symbol-set -> target) edge instead of one entry per (symbol, target) pair.  A state that self-loops on all
+// 256 symbols is 1 record instead of 256 CSR entries (the FPGA streams all 256 through its 4-lane compare,
+// Design/FPGA.v:227-407).  record = a[7:0] | b[15:8] | is_class[16] | set_id[31:17] | target[55:32]
+//   pair  : edge taken iff c == a or c == b;   class : iff bit c of memb[set_id] (256-bit bitmap) is set
+struct Ecsr {
+    std::vector<uint32_t> eptr;    // [n_states + 1]; eptr[s] == eptr[s+1]  <=>  accepting (zero out-degree)
+    std::vector<uint64_t> erec;    // [n_edges]
+    std::vector<uint32_t> memb;    // [n_sets * 8]
+    uint32_t n_sets = 0;
+};
+int ecsr_build(const Nfa &nfa, Ecsr &out, std::string &err);   // includes an exhaustive check against the CSR
+
 // ---- image.cpp --------------------------------------------------------------------------------
 // Execution image: the CSR re-indexed at load time for the lane kernel (one thread per stream).
 // See DESIGN.md "Execution image" for the layout; image_successors() is its executable definition

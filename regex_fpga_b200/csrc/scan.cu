@@ -336,8 +336,9 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
     uint32_t *list_cur = bits_nxt + nw;
     uint32_t *list_nxt = list_cur + WARP_LCAP;
     uint32_t *n_next = list_nxt + WARP_LCAP;
-    const uint32_t *__restrict__ rp = nfa.row_ptr;
-    const uint32_t *__restrict__ tr = nfa.trans;
+    const uint32_t *__restrict__ ep = nfa.eptr;
+    const unsigned long long *__restrict__ er = nfa.erec;
+    const uint32_t *__restrict__ em = nfa.emembs;
 
     for (uint32_t w = lane; w < 2 * nw; w += 32) bits_cur[w] = 0;
     __syncwarp();
@@ -379,34 +380,41 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
             if (lane == 0) *n_next = 0;
             __syncwarp();
             const bool report = k >= emit_from;
-            if (!dense) {
-                for (uint32_t base = 0; base < ncur; base += 32) {
-                    const uint32_t i = base + lane;
-                    const bool valid = i < ncur;
-                    uint32_t s = 0, r0 = 0, r1 = 0;
-                    if (valid) { s = list_cur[i]; r0 = rp[s]; r1 = rp[s + 1]; }
-                    const uint32_t len = r1 - r0;
-                    if (valid && len == 0 && report) emit_match(out, sid + batch.stream_id_base, k, s);   // FPGA.v:210-226
-                    const bool is_long = valid && len > 8;
-                    if (valid && !is_long)
-                        for (uint32_t j = r0; j < r1; j++) { const uint32_t w = tr[j]; if ((w >> 24) == c) insert(w & 0xFFFFFFu); }
-                    uint32_t big = __ballot_sync(0xffffffffu, is_long);
-                    while (big) {   // one long row at a time, 32 transitions per pass (FPGA.v:227-407 does 4)
-                        const int l = __ffs((int)big) - 1;
-                        big &= big - 1;
-                        const uint32_t R0 = __shfl_sync(0xffffffffu, r0, l), R1 = __shfl_sync(0xffffffffu, r1, l);
-                        for (uint32_t j = R0 + lane; j < R1; j += 32) { const uint32_t w = tr[j]; if ((w >> 24) == c) insert(w & 0xFFFFFFu); }
+            // expand S_k through the edge-grouped rows: one active state per lane, its few edges serially
+            auto expand = [&](uint32_t s) {
+                const uint32_t e0 = ep[s], e1 = ep[s + 1];
+                if (e0 == e1) { if (report) emit_match(out, sid + batch.stream_id_base, k, s); return; }   // FPGA.v:210-226
+                for (uint32_t j = e0; j < e1; j++) {
+                    const unsigned long long r = er[j];
+                    const uint32_t lo = (uint32_t)r;
+                    const bool hit = (lo & 0x10000u) ? ((em[(lo >> 17) * 8 + (c >> 5)] >> (c & 31)) & 1u) != 0
+                                                     : (c == (lo & 0xFFu) || c == ((lo >> 8) & 0xFFu));
+                    if (hit) insert((uint32_t)(r >> 32));
+                }
+            };
+            if (!dense && ncur <= 8) {
+                // few active states: the 32 lanes share each state's edges (coalesced record loads)
+                for (uint32_t i = 0; i < ncur; i++) {
+                    const uint32_t s = list_cur[i];
+                    const uint32_t e0 = ep[s], e1 = ep[s + 1];
+                    if (e0 == e1 && report && lane == 0) emit_match(out, sid + batch.stream_id_base, k, s);   // FPGA.v:210-226
+                    for (uint32_t j = e0 + lane; j < e1; j += 32) {
+                        const unsigned long long r = er[j];
+                        const uint32_t lo = (uint32_t)r;
+                        const bool hit = (lo & 0x10000u) ? ((em[(lo >> 17) * 8 + (c >> 5)] >> (c & 31)) & 1u) != 0
+                                                         : (c == (lo & 0xFFu) || c == ((lo >> 8) & 0xFFu));
+                        if (hit) insert((uint32_t)(r >> 32));
                     }
                 }
+            } else if (!dense) {
+                for (uint32_t i = lane; i < ncur; i += 32) expand(list_cur[i]);
             } else {
                 for (uint32_t wd = lane; wd < nw; wd += 32) {
                     uint32_t bits = bits_cur[wd];
                     while (bits) {
                         const uint32_t s = wd * 32 + (uint32_t)__ffs((int)bits) - 1u;
                         bits &= bits - 1;
-                        const uint32_t r0 = rp[s], r1 = rp[s + 1];
-                        if (r0 == r1 && report) emit_match(out, sid + batch.stream_id_base, k, s);
-                        for (uint32_t j = r0; j < r1; j++) { const uint32_t w = tr[j]; if ((w >> 24) == c) insert(w & 0xFFFFFFu); }
+                        expand(s);
                     }
                 }
             }

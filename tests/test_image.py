@@ -86,3 +86,45 @@ def test_adversarial_prefixes_reach_long_lived_states(snort):
     from regex_fpga_b200 import workloads as WL
     pref = WL.adversarial_prefixes(snort.entries, snort.n_states)
     assert len(pref) >= 40 and all(1 <= p.size < 200 for p in pref)
+
+
+def test_hypothesis_random_nfas_verify():
+    """Property-based: any well-formed CSR image (arbitrary rows, self-loops, fan-out, accept states, a start state
+    that may itself be sticky or accepting) yields an execution image that passes the exhaustive verifier, or is
+    cleanly reported as general-kernel-only."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @st.composite
+    def nfas(draw):
+        n = draw(st.integers(1, 24))
+        rows = []
+        for s in range(n):
+            kind = draw(st.integers(0, 5))
+            r = []
+            if kind == 0:
+                pass                                                   # accepting
+            elif kind == 1:                                            # sticky-ish: long self loop + exits
+                lo = draw(st.integers(0, 200))
+                r += [(c, s) for c in range(lo, min(256, lo + draw(st.integers(16, 256))))]
+                for _ in range(draw(st.integers(0, 3))):
+                    r.append((draw(st.integers(0, 255)), draw(st.integers(0, n - 1)) or min(1, n - 1)))
+            else:
+                for _ in range(draw(st.integers(1, 6))):
+                    c = draw(st.integers(0, 255))
+                    t = draw(st.integers(0, n - 1))
+                    if t == 0:
+                        t = min(1, n - 1)                              # nothing targets state 0 in the shipped images
+                    r.append((c, t))
+                    if draw(st.booleans()):
+                        r.append((c ^ 0x20, t))
+            rows.append([(c, t) for c, t in r if not (t == 0 and n > 1)])
+        return rows
+
+    @settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(nfas(), st.sampled_from([(0, 0), (1, 2), (2, 4)]))
+    def check(rows, opt):
+        E, n = build_entries(rows)
+        info = R.image_check(E, n, opt[0], opt[1])
+        assert info["n_states"] == n and info["image_ok"] == 1
+
+    check()
