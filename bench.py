@@ -42,6 +42,17 @@ def load_ruleset(name="snort_16"):
     return z["entries"], int(z["n_states"]), z["lo"], z["hi"]
 
 
+def measured_traffic(sym_per_launch):
+    """DRAM bytes per launch of the lane kernel from the committed ncu capture (profiles/r1_traffic.json), scaled by
+    the symbols one launch processes; None when the capture is absent."""
+    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        t = json.load(open(p))
+        return int(round(t["dram_bytes_per_symbol"] * sym_per_launch))
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -284,7 +295,8 @@ def ours_arm(args, rank, world, local_rank):
             "e2e": e2e,
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "kernel": "scan_lane_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(sym_per_step),
+                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_traffic.json)", "peak_source": peak_src,
                          "frac_of_8000": achieved / 8000.0, "scan_ms": scan_ms,
                          "algorithmic_bytes_per_launch": sym_per_step},
             "matches_per_step_rank0": n_matches, "rescanned_streams": n_rescanned, "records_dropped": n_dropped,
