@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RFB_ABI_VERSION 1
+#define RFB_ABI_VERSION 2
 
 typedef enum rfb_status {
     RFB_OK = 0,
@@ -79,8 +79,19 @@ typedef struct rfb_batch {
     uint32_t n_steps;          /* symbol steps per stream when steps == NULL */
     const uint32_t *steps;     /* optional per-stream step counts (ragged batches) */
     uint32_t stream_id_base;   /* added to the stream field of every record (sharded jobs) */
+    uint32_t pos_base;         /* added to the pos field of every record (resumed streams) */
+    /* Resumable scans -- the software form of the input_char_flag handshake (Design/FPGA.v:125,740,763): the
+     * design is a streaming device whose only carry-over state is the active set.  Per stream, state_stride =
+     * 1 + state_cap 32-bit words: word 0 = number of active states, words 1.. = their state ids (any order).
+     * state_in  == NULL: every stream starts from the reset state {0} (Design/FPGA.v:146-147).
+     * state_out == NULL: the final set S_{n_steps} is discarded, as the testbench does (TB:71-86).
+     * A final set with more than state_cap members is reported as count 0xFFFFFFFF (RFB_STATE_OVERFLOW). */
+    const uint32_t *state_in;
+    uint32_t *state_out;
+    uint32_t state_cap;
     uint32_t reserved;
 } rfb_batch;
+#define RFB_STATE_OVERFLOW 0xFFFFFFFFu
 
 /* flags for rfb_scan / rfb_scan_device */
 #define RFB_SCAN_DEFAULT      0u

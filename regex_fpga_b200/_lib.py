@@ -19,7 +19,9 @@ class rfb_nfa_info(C.Structure):
 class rfb_batch(C.Structure):
     _fields_ = [("data", C.c_void_p), ("data_bytes", C.c_uint64), ("n_streams", C.c_uint64),
                 ("stride", C.c_uint64), ("offsets", C.c_void_p), ("n_steps", C.c_uint32),
-                ("steps", C.c_void_p), ("stream_id_base", C.c_uint32), ("reserved", C.c_uint32)]
+                ("steps", C.c_void_p), ("stream_id_base", C.c_uint32), ("pos_base", C.c_uint32),
+                ("state_in", C.c_void_p), ("state_out", C.c_void_p), ("state_cap", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class rfb_result(C.Structure):

@@ -48,6 +48,8 @@ struct rfb_nfa {
     uint32_t *d_eptr = nullptr; unsigned long long *d_erec = nullptr; uint32_t *d_emembs = nullptr;
     uint8_t *d_blob = nullptr;
     uint32_t *d_orig = nullptr;
+    uint32_t *d_idof = nullptr, *d_virt_ptr = nullptr, *d_virt_ids = nullptr;
+    uint32_t *d_state_in = nullptr, *d_state_out = nullptr; size_t d_state_cap_words = 0;   // rfb_scan staging
 };
 
 static int fail(rfb_ctx *ctx, int code, const std::string &msg) {
@@ -214,6 +216,21 @@ int rfb_nfa_from_entries(rfb_ctx *ctx, const uint32_t *entries, size_t n_entries
             rfb_nfa_destroy(nfa);
             return cuda_fail(ctx, e, "upload execution image");
         }
+        {   // id maps for resumable scans
+            std::vector<uint32_t> vptr(1, 0), vids;
+            for (const auto &v : im.virt_of_cls1) { vids.insert(vids.end(), v.begin(), v.end()); vptr.push_back((uint32_t)vids.size()); }
+            if (vptr.size() < 2) vptr.push_back(0);
+            if ((e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_idof), im.id_of_orig.size() * 4)) != cudaSuccess ||
+                (e = cudaMemcpy(nfa->d_idof, im.id_of_orig.data(), im.id_of_orig.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+                (e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_virt_ptr), vptr.size() * 4)) != cudaSuccess ||
+                (e = cudaMemcpy(nfa->d_virt_ptr, vptr.data(), vptr.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
+                (e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_virt_ids), std::max<size_t>(1, vids.size()) * 4)) != cudaSuccess ||
+                (e = cudaMemcpy(nfa->d_virt_ids, vids.data(), vids.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+                rfb_nfa_destroy(nfa);
+                return cuda_fail(ctx, e, "upload id maps");
+            }
+            nfa->dev.id_of_orig = nfa->d_idof; nfa->dev.virt_ptr = nfa->d_virt_ptr; nfa->dev.virt_ids = nfa->d_virt_ids;
+        }
         nfa->dev.blob = nfa->d_blob;
         nfa->dev.orig_of_id = nfa->d_orig;
         nfa->dev.h = im.h;
@@ -236,6 +253,8 @@ void rfb_nfa_destroy(rfb_nfa *nfa) {
     cudaSetDevice(nfa->device);
     cudaFree(nfa->d_entries); cudaFree(nfa->d_blob); cudaFree(nfa->d_orig);
     cudaFree(nfa->d_eptr); cudaFree(nfa->d_erec); cudaFree(nfa->d_emembs);
+    cudaFree(nfa->d_idof); cudaFree(nfa->d_virt_ptr); cudaFree(nfa->d_virt_ids);
+    cudaFree(nfa->d_state_in); cudaFree(nfa->d_state_out);
     delete nfa;
 }
 
@@ -321,6 +340,7 @@ static int check_batch(rfb_ctx *ctx, const rfb_batch *b, bool host) {
     if (!b) return fail(ctx, RFB_E_INVALID, "batch is NULL");
     if (b->n_streams > 0xFFFFFFFFull) return fail(ctx, RFB_E_INVALID, "n_streams exceeds 2^32-1 (stream ids are 32-bit)");
     if (b->n_streams && !b->data && b->data_bytes) return fail(ctx, RFB_E_INVALID, "data is NULL");
+    if ((b->state_in || b->state_out) && (b->state_cap == 0 || b->state_cap > 255)) return fail(ctx, RFB_E_INVALID, "state_cap must be 1..255 when state_in/state_out are used");
     if (host) {  // host pointers can be bounds-checked
         for (uint64_t s = 0; s < b->n_streams; s++) {
             const uint64_t off = b->offsets ? b->offsets[s] : s * b->stride;
@@ -359,6 +379,7 @@ static int enqueue_kernels(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b,
     bd.offsets = reinterpret_cast<const unsigned long long *>(b->offsets);
     bd.steps = b->steps; bd.n_steps = b->n_steps; bd.stream_id_base = b->stream_id_base;
     bd.chunk_streams = chunk_streams; bd.ready = &ctx->g->chunks_ready;
+    bd.pos_base = b->pos_base; bd.state_cap = b->state_cap; bd.state_in = b->state_in; bd.state_out = b->state_out;
     OutDev od;
     od.counts = (flags & RFB_SCAN_NO_COUNTS) ? nullptr : reinterpret_cast<unsigned long long *>(res->counts);
     od.records = res->records; od.capacity = res->records ? res->record_capacity : 0;
@@ -429,6 +450,16 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
         CU(ctx, cudaMemcpyAsync(ctx->d_steps, b->steps, b->n_streams * 4, cudaMemcpyHostToDevice, st));
         db.steps = ctx->d_steps;
     }
+    const size_t state_words = (size_t)b->n_streams * (1 + (size_t)b->state_cap);
+    rfb_nfa *mnfa = const_cast<rfb_nfa *>(nfa);   // staging buffers live with the NFA handle
+    if ((b->state_in || b->state_out) && mnfa->d_state_cap_words < state_words) {
+        cudaFree(mnfa->d_state_in); cudaFree(mnfa->d_state_out); mnfa->d_state_in = mnfa->d_state_out = nullptr; mnfa->d_state_cap_words = 0;
+        CU(ctx, cudaMalloc(reinterpret_cast<void **>(&mnfa->d_state_in), std::max<size_t>(16, state_words) * 4));
+        CU(ctx, cudaMalloc(reinterpret_cast<void **>(&mnfa->d_state_out), std::max<size_t>(16, state_words) * 4));
+        mnfa->d_state_cap_words = state_words;
+    }
+    if (b->state_in) { CU(ctx, cudaMemcpyAsync(mnfa->d_state_in, b->state_in, state_words * 4, cudaMemcpyHostToDevice, st)); db.state_in = mnfa->d_state_in; }
+    if (b->state_out) db.state_out = mnfa->d_state_out;
     rfb_result dr = *res;
     const bool want_counts = res->counts && !(flags & RFB_SCAN_NO_COUNTS);
     if (want_counts) {
@@ -485,6 +516,7 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     if (rc) return rc;
     if (want_counts) CU(ctx, cudaMemcpyAsync(res->counts, ctx->d_counts, (size_t)nfa->host.n_states * 8, cudaMemcpyDeviceToHost, st));
     if (dr.n_records) CU(ctx, cudaMemcpyAsync(res->records, ctx->d_records, dr.n_records * sizeof(rfb_match), cudaMemcpyDeviceToHost, st));
+    if (b->state_out && state_words) CU(ctx, cudaMemcpyAsync(b->state_out, mnfa->d_state_out, state_words * 4, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     res->n_matches = dr.n_matches; res->n_records = dr.n_records; res->n_dropped = dr.n_dropped;
     res->n_symbols = dr.n_symbols; res->n_rescanned = dr.n_rescanned; res->gpu_ms = dr.gpu_ms;

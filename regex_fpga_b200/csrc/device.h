@@ -29,6 +29,11 @@ struct BatchDev {
     // rfb_scan only: streams [c*chunk_streams, (c+1)*chunk_streams) become readable when *ready > c (0: no gating)
     unsigned int chunk_streams;
     const unsigned int *ready;
+    // resumable scans: per-stream active sets in / out (original state ids), stride 1 + state_cap words
+    unsigned int pos_base;
+    unsigned int state_cap;
+    const unsigned int *state_in;
+    unsigned int *state_out;
 };
 
 struct OutDev {
@@ -50,6 +55,9 @@ struct NfaDev {
     // execution image
     const uint8_t *blob;         // ImageHeader::blob_bytes bytes, 16-byte aligned
     const uint32_t *orig_of_id;  // [n_slots]
+    const uint32_t *id_of_orig;  // [n_states]
+    const uint32_t *virt_ptr;    // [n_cls1 + 1]: never-materialised targets of the accelerated state per cls1 ...
+    const uint32_t *virt_ids;    // ... as original state ids
     ImageHeader h;
 };
 

@@ -97,6 +97,40 @@ __device__ __noinline__ bool ring_contains(uint32_t lb, uint32_t from, uint32_t 
     return false;
 }
 
+// ---- resumable scans: per-stream active sets as original state ids (rare paths, kept out of line) ----
+// S_{n_steps} of a finished stream = sticky bits + the ring's new entries + the never-materialised targets of the
+// accelerated state for the last symbol (cls1 = pcls).
+__device__ __noinline__ void lane_export_state(const uint32_t *orig_of_id, const uint32_t *virt_ptr, const uint32_t *virt_ids,
+                                               unsigned int *dst, uint32_t cap, uint64_t P0, uint64_t P1, uint32_t lb,
+                                               uint32_t from, uint32_t to, uint32_t row, uint32_t rmask, uint32_t pcls) {
+    uint32_t n = 0;
+    for (int w = 0; w < 2; w++) {
+        uint64_t bits = w ? P1 : P0;
+        while (bits) {
+            const uint32_t b = (uint32_t)__ffsll((long long)bits) - 1u + 64u * w;
+            bits &= bits - 1;
+            if (n < cap) dst[1 + n] = orig_of_id[b];
+            n++;
+        }
+    }
+    for (uint32_t o = from; o != to; o = (o + row) & rmask) {
+        if (n < cap) dst[1 + n] = orig_of_id[ring_ld(lb + o)];
+        n++;
+    }
+    if (pcls) for (uint32_t j = virt_ptr[pcls]; j < virt_ptr[pcls + 1]; j++) {
+        if (n < cap) dst[1 + n] = virt_ids[j];
+        n++;
+    }
+    dst[0] = n <= cap ? n : 0xFFFFFFFFu;
+}
+// a stream without steps keeps its state
+__device__ __noinline__ void carry_state(const unsigned int *src, unsigned int *dst, uint32_t cap) {
+    if (!src) { dst[0] = 1; dst[1] = 0; return; }
+    const uint32_t n = src[0];
+    dst[0] = n;
+    for (uint32_t i = 0; i < n && i < cap; i++) dst[1 + i] = src[1 + i];
+}
+
 template <int W, int RING_CAP>
 __global__ void __launch_bounds__(LANE_THREADS, 1)
 scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
@@ -159,7 +193,12 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                         out.rescan[slot] = make_uint2(sid, k);
                     }
                     have = false; ovf = false;
-                } else if (k == nsteps) have = false;
+                } else if (k == nsteps) {
+                    if (batch.state_out)
+                        lane_export_state(nfa.orig_of_id, nfa.virt_ptr, nfa.virt_ids, batch.state_out + (size_t)sid * (1u + batch.state_cap),
+                                          batch.state_cap, P0, P1, lb, rp, re, ROW, RMASK, pcls);
+                    have = false;
+                }
             }
             if (!have) {   // ---- next stream ----
                 for (;;) {
@@ -167,6 +206,9 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     if (sid >= batch.n_streams) break;
                     nsteps = batch.steps ? batch.steps[sid] : batch.n_steps;
                     if (nsteps) break;
+                    if (batch.state_out)
+                        carry_state(batch.state_in ? batch.state_in + (size_t)sid * (1u + batch.state_cap) : nullptr,
+                                    batch.state_out + (size_t)sid * (1u + batch.state_cap), batch.state_cap);
                 }
                 if (sid >= batch.n_streams) { done = true; break; }   // this lane is done
                 if (batch.steps) atomicAdd(&out.g->n_symbols, (unsigned long long)nsteps);
@@ -175,7 +217,23 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     while (*reinterpret_cast<const volatile unsigned int *>(batch.ready) < need) __nanosleep(256);
                 }
                 P0 = 0; P1 = 0; Pn0 = 0; Pn1 = 0; rp = 0; re = 0; wp = 0; flo = 0; fhi = 0; pcls = 0; k = 0;
-                if (h.start_id < nsb) {                                               // Design/FPGA.v:146-147
+                if (batch.state_in) {   // resume: the stream's active set as left by an earlier call
+                    const unsigned int *stt = batch.state_in + (size_t)sid * (1u + batch.state_cap);
+                    const uint32_t ns = min(stt[0], batch.state_cap);
+                    bool fits = true;
+                    for (uint32_t q = 0; q < ns; q++) {
+                        const uint32_t id = nfa.id_of_orig[stt[1 + q]];
+                        if (id < nsb) { if (W == 1 || id < 64) P0 |= 1ull << (id & 63); else P1 |= 1ull << (id & 63); }
+                        else if (((wp + ROW) & RMASK) == rp) fits = false;
+                        else { ring_st(lb + wp, id); wp = (wp + ROW) & RMASK; }
+                    }
+                    re = wp;
+                    if (!fits) {   // more transient members than the ring holds: the general kernel takes the whole stream
+                        const unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
+                        out.rescan[slot] = make_uint2(sid, 0u);
+                        continue;
+                    }
+                } else if (h.start_id < nsb) {                                        // Design/FPGA.v:146-147
                     if (W == 1 || h.start_id < 64) P0 = 1ull << (h.start_id & 63); else P1 = 1ull << (h.start_id & 63);
                 } else { ring_st(lb, h.start_id); re = ROW; wp = ROW; }
                 // input: aligned 16-byte chunks kept in registers, the first one shifted to the stream's first byte
@@ -253,7 +311,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     idx = u + (u >= gbase ? hc : 0u);
                     look = true;
                     if (u - acc_base < n_acc) {                   // accepting (Design/FPGA.v:210-226)
-                        emit_match_cold(out, sid + batch.stream_id_base, k, nfa.orig_of_id[u]);
+                        emit_match_cold(out, sid + batch.stream_id_base, k + batch.pos_base, nfa.orig_of_id[u]);
                         look = false;
                     }
                 } else {                                          // row of a firing sticky state
@@ -373,7 +431,11 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
 
         uint32_t ncur = 1;
         bool dense = false;
-        if (lane == 0) list_cur[0] = 0;                                   // Design/FPGA.v:146-147
+        if (batch.state_in) {   // resume from the set an earlier call left
+            const unsigned int *stt = batch.state_in + (size_t)sid * (1u + batch.state_cap);
+            ncur = min(stt[0], batch.state_cap);
+            for (uint32_t i = lane; i < ncur; i += 32) list_cur[i] = stt[1 + i];
+        } else if (lane == 0) list_cur[0] = 0;                            // Design/FPGA.v:146-147
         __syncwarp();
         for (uint32_t k = 0; k < nsteps; k++) {
             const uint32_t c = __ldg(sp + k);
@@ -383,7 +445,7 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
             // expand S_k through the edge-grouped rows: one active state per lane, its few edges serially
             auto expand = [&](uint32_t s) {
                 const uint32_t e0 = ep[s], e1 = ep[s + 1];
-                if (e0 == e1) { if (report) emit_match(out, sid + batch.stream_id_base, k, s); return; }   // FPGA.v:210-226
+                if (e0 == e1) { if (report) emit_match(out, sid + batch.stream_id_base, k + batch.pos_base, s); return; }   // FPGA.v:210-226
                 for (uint32_t j = e0; j < e1; j++) {
                     const unsigned long long r = er[j];
                     const uint32_t lo = (uint32_t)r;
@@ -397,7 +459,7 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
                 for (uint32_t i = 0; i < ncur; i++) {
                     const uint32_t s = list_cur[i];
                     const uint32_t e0 = ep[s], e1 = ep[s + 1];
-                    if (e0 == e1 && report && lane == 0) emit_match(out, sid + batch.stream_id_base, k, s);   // FPGA.v:210-226
+                    if (e0 == e1 && report && lane == 0) emit_match(out, sid + batch.stream_id_base, k + batch.pos_base, s);   // FPGA.v:210-226
                     for (uint32_t j = e0 + lane; j < e1; j += 32) {
                         const unsigned long long r = er[j];
                         const uint32_t lo = (uint32_t)r;
@@ -428,6 +490,12 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
             uint32_t *tb = bits_cur; bits_cur = bits_nxt; bits_nxt = tb;
             uint32_t *tl = list_cur; list_cur = list_nxt; list_nxt = tl;
             __syncwarp();
+        }
+        if (batch.state_out) {   // S_{n_steps}: handed to the caller instead of being dropped
+            unsigned int *dst = batch.state_out + (size_t)sid * (1u + batch.state_cap);
+            const bool fits = !dense && ncur <= batch.state_cap;
+            if (lane == 0) dst[0] = fits ? ncur : 0xFFFFFFFFu;
+            if (fits) for (uint32_t i = lane; i < ncur; i += 32) dst[1 + i] = list_cur[i];
         }
         // leave both bit vectors clean for the next stream (S_{n_steps} is never examined, TB:71-86)
         if (!dense) { for (uint32_t i = lane; i < ncur; i += 32) bits_cur[list_cur[i] >> 5] = 0; }

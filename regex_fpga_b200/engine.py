@@ -134,10 +134,14 @@ class Context:
         return Nfa(self, h)
 
 
+STATE_OVERFLOW = 0xFFFFFFFF
+
+
 class ScanResult:
-    def __init__(self, counts, records, res):
+    def __init__(self, counts, records, res, state=None):
         self.counts = counts
         self.records = records
+        self.state = state      # (n_streams, 1 + state_cap) uint32: [count, ids...] per stream, when requested
         self.n_matches = int(res.n_matches)
         self.n_records = int(res.n_records)
         self.n_dropped = int(res.n_dropped)
@@ -178,7 +182,10 @@ class Nfa:
 
     # -- host buffers in, host results out (H2D + kernels + D2H inside the call) --
     def scan(self, data, n_streams, n_steps=0, stride=0, offsets=None, steps=None, record_capacity=1 << 20,
-             flags=SCAN_SORT_RECORDS, stream_id_base=0, want_counts=True):
+             flags=SCAN_SORT_RECORDS, stream_id_base=0, want_counts=True, state_in=None, want_state=False,
+             state_cap=63, pos_base=0):
+        """state_in / want_state: resumable scans -- pass the `state` of the previous call's result to continue the
+        same streams (and pos_base = symbols already consumed) instead of starting from the reset state {0}."""
         data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
         b = rfb_batch()
         b.data = data.ctypes.data if data.size else None
@@ -198,6 +205,19 @@ class Nfa:
             assert steps.size == n_streams
             b.steps = steps.ctypes.data
             keep.append(steps)
+        b.pos_base = pos_base
+        state_out = None
+        if state_in is not None:
+            state_in = np.ascontiguousarray(state_in, dtype=np.uint32)
+            assert state_in.shape[0] == n_streams and state_in.ndim == 2
+            state_cap = state_in.shape[1] - 1
+            b.state_in = state_in.ctypes.data
+            keep.append(state_in)
+        if want_state:
+            state_out = np.zeros((n_streams, 1 + state_cap), dtype=np.uint32)
+            b.state_out = state_out.ctypes.data
+        if state_in is not None or want_state:
+            b.state_cap = state_cap
         counts = np.zeros(self.n_states, dtype=np.uint64) if want_counts else None
         records = np.zeros(record_capacity, dtype=MATCH_DTYPE)
         r = rfb_result()
@@ -205,12 +225,12 @@ class Nfa:
         r.records = records.ctypes.data if record_capacity else None
         r.record_capacity = record_capacity
         _check(self._L.rfb_scan(self.ctx._h, self._h, C.byref(b), flags, C.byref(r)), self.ctx._h)
-        return ScanResult(counts, records[: r.n_records], r)
+        return ScanResult(counts, records[: r.n_records], r, state_out)
 
     # -- device pointers in, device results out (for benchmarks: no PCIe in the timed region) --
     def scan_device(self, data_ptr, data_bytes, n_streams, n_steps, stride, counts_ptr=None, records_ptr=None,
                     record_capacity=0, flags=0, cuda_stream=None, offsets_ptr=None, steps_ptr=None,
-                    stream_id_base=0):
+                    stream_id_base=0, state_in_ptr=None, state_out_ptr=None, state_cap=0, pos_base=0):
         b = rfb_batch()
         b.data = data_ptr
         b.data_bytes = data_bytes
@@ -220,6 +240,10 @@ class Nfa:
         b.offsets = offsets_ptr
         b.steps = steps_ptr
         b.stream_id_base = stream_id_base
+        b.pos_base = pos_base
+        b.state_in = state_in_ptr
+        b.state_out = state_out_ptr
+        b.state_cap = state_cap
         r = rfb_result()
         r.counts = counts_ptr
         r.records = records_ptr

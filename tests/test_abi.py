@@ -24,13 +24,13 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == names, "python binding and header disagree"
-    assert _lib.load().rfb_abi_version() == 1
+    assert _lib.load().rfb_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.rfb_match) == 12
     assert ctypes.sizeof(_lib.rfb_nfa_info) == 48
-    assert ctypes.sizeof(_lib.rfb_batch) == 64
+    assert ctypes.sizeof(_lib.rfb_batch) == 88
     assert ctypes.sizeof(_lib.rfb_result) == 72
 
 

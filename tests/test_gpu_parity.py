@@ -235,6 +235,71 @@ def test_fpga_cycles_and_tb_report(gpu_ctx, snort, l7, expected, name, tmp_path)
     assert out[-1] == f"Total no. cycles: {O.cycle_model(rs.entries, rs.n_states, rs.lo, rs.hi, 3000)}"
 
 
+@pytest.mark.parametrize("kernel,flags", KERNELS)
+def test_resumable_scan_equals_one_shot(gpu_ctx, snort, l7, kernel, flags):
+    """the design is a streaming device (input_char_flag handshake, FPGA.v:125,740,763) whose only
+    carry-over state is the active set.  Cutting streams at arbitrary points and resuming from the exported sets
+    must reproduce the one-shot scan exactly: same records (pos_base added), same counts."""
+    rng = np.random.default_rng(3)
+    for rs in (snort, l7):
+        nfa = gpu_ctx.nfa_from_entries(rs.entries)
+        n, L = 64, 4000
+        data = np.stack([(rs.hi if s & 1 else rs.lo)[s * 700: s * 700 + L] for s in range(n)])
+        whole = nfa.scan(data, n, n_steps=L, stride=L, flags=flags)
+        cuts = [0] + sorted(rng.choice(np.arange(1, L), size=5, replace=False).tolist()) + [L]
+        cuts.insert(3, cuts[3])                                     # an empty chunk in the middle
+        state, counts, recs = None, np.zeros(rs.n_states, np.uint64), []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            part = nfa.scan(np.ascontiguousarray(data[:, a:b]) if b > a else np.zeros((n, 1), np.uint8), n,
+                            n_steps=b - a, stride=max(b - a, 1), flags=flags, state_in=state, want_state=True,
+                            pos_base=a, state_cap=127)
+            assert not np.any(part.state[:, 0] == R.STATE_OVERFLOW)
+            state = part.state
+            counts += part.counts
+            recs += recs_tuple(part.records)
+        assert np.array_equal(counts, whole.counts)
+        assert sorted(recs) == recs_tuple(whole.records)
+        # the exported set is S_{n_steps} in the reference's state numbering: compare with the oracle's next sets
+        for s in (0, 1, 33):
+            want = set()
+            cur = {0}
+            rp = rs.entries[: rs.n_states + 1]
+            tr = rs.entries[rs.n_states + 1:]
+            for k in range(cuts[1]):
+                c = data[s, k]
+                nxt = set()
+                for st_ in cur:
+                    row = tr[rp[st_]: rp[st_ + 1]]
+                    nxt.update((row[(row >> 24) == c] & 0xFFFFFF).tolist())
+                cur = nxt
+            want = cur
+            first = nfa.scan(np.ascontiguousarray(data[:, : cuts[1]]), n, n_steps=cuts[1], stride=cuts[1], flags=flags,
+                             want_state=True, state_cap=127).state
+            assert set(first[s, 1: 1 + first[s, 0]].tolist()) == want
+
+
+def test_resume_with_more_states_than_the_ring_holds(gpu_ctx):
+    """A resumed set larger than the lane kernel's ring goes to the general kernel from step 0; an exported set
+    larger than state_cap is flagged, not truncated."""
+    n = 80
+    rows = [[(1, s) for s in range(1, n - 1)]]
+    for s in range(1, n - 1):
+        rows.append([(1, s + 1 if s + 1 < n - 1 else 1), (2, n - 1)])
+    rows.append([])
+    E, ns = build_entries(rows)
+    nfa = gpu_ctx.nfa_from_entries(E, ns)
+    d = np.ones((8, 40), np.uint8)
+    d[:, 30] = 2
+    whole = nfa.scan(d, 8, n_steps=40, stride=40)
+    a = nfa.scan(np.ascontiguousarray(d[:, :10]), 8, n_steps=10, stride=10, want_state=True, state_cap=100)
+    assert np.all(a.state[:, 0] == n - 2)                           # 78 active states: more than the ring's 31..63
+    b = nfa.scan(np.ascontiguousarray(d[:, 10:]), 8, n_steps=30, stride=30, state_in=a.state, pos_base=10)
+    assert sorted(recs_tuple(a.records) + recs_tuple(b.records)) == recs_tuple(whole.records)
+    assert b.n_rescanned == 8
+    small = nfa.scan(np.ascontiguousarray(d[:, :10]), 8, n_steps=10, stride=10, want_state=True, state_cap=16)
+    assert np.all(small.state[:, 0] == R.STATE_OVERFLOW)
+
+
 def test_config5_replicated_large_nfa_adversarial(gpu_ctx, snort):
     """BASELINE config 5: 7 x snort_16 behind one start state (66 592 states, beyond the FPGA's own 16-bit
     rd_address) with adversarial high-activity streams and hi-trace windows.  Too large for the 15-bit ids of
