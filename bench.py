@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 STREAM_LEN = 1500
 STRIDE = 1536
 SEED = 0x5EED0001
-METRIC = "gbit_per_s_scanned_snort16"
+METRIC = "gbit_per_s_scanned_snort16"   # BASELINE.json: Gbit/s scanned (snort_16 NFA)
 
 
 def load_ruleset(name="snort_16"):
@@ -139,7 +139,7 @@ def reference_arm(args, rank, world):
         return
     from oracle import oracle_py as O
     O.build()
-    E, n_states, lo, hi = load_ruleset()
+    E, n_states, lo, hi = load_ruleset(args.ruleset)
     threads = os.cpu_count() or 1
     n_pairs = max(threads, 8)
     times, syms, cycles = [], 0, 0
@@ -167,7 +167,9 @@ def reference_arm(args, rank, world):
 
 
 def workload_config(args, world):
-    return {"workload": f"snort_16 NFA (9514 states, 79856 transitions) over {args.streams} synthetic "
+    nfa_desc = {"snort_16": "snort_16 NFA (9514 states, 79856 transitions)",
+                "l7_filter": "l7-filter NFA (2794 states, 124977 transitions)"}[args.ruleset]
+    return {"workload": f"{nfa_desc} over {args.streams} synthetic "
                         f"{STREAM_LEN}-byte packet streams per GPU ({args.mix}: windows of the shipped lo/hi "
                         f"traces at splitmix64 offsets, seed {SEED:#x})",
             "streams_per_gpu": args.streams, "streams_total": args.streams * world, "stream_bytes": STREAM_LEN,
@@ -219,7 +221,7 @@ def ours_arm(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device(dev))
-    E, n_states, lo, hi = load_ruleset()
+    E, n_states, lo, hi = load_ruleset(args.ruleset)
     ctx = R.Context(local_rank)
     nfa = ctx.nfa_from_entries(E)
     n = args.streams
@@ -335,6 +337,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mix", default="wmix", choices=["wmix", "whi", "wlo", "uniform", "adv"])
+    ap.add_argument("--ruleset", default="snort_16", choices=["snort_16", "l7_filter"],
+                    help="snort_16 is the headline (BASELINE.json); l7_filter is the reference's other shipped image")
     ap.add_argument("--streams", type=int, default=1 << 20, help="streams per GPU")
     ap.add_argument("--record-capacity", type=int, default=1 << 22)
     ap.add_argument("--e2e-steps", type=int, default=3)
