@@ -37,6 +37,10 @@ SEED = 0x5EED0001
 METRIC = "gbit_per_s_scanned_snort16"   # BASELINE.json: Gbit/s scanned (snort_16 NFA)
 
 
+def metric_name(args):
+    return METRIC if args.ruleset == "snort_16" else "gbit_per_s_scanned_" + args.ruleset
+
+
 def load_ruleset(name="snort_16"):
     z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
     return z["entries"], int(z["n_states"]), z["lo"], z["hi"]
@@ -152,7 +156,7 @@ def reference_arm(args, rank, world):
     gbit = syms * 8 / total / 1e9
     desc = f"{n_pairs} (lo,hi) stream pairs x {STREAM_LEN} entries per step ({2 * n_pairs * (STREAM_LEN - 1)} symbols)"
     line = {
-        "impl": "reference", "metric": METRIC, "value": gbit, "unit": "Gbit/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": metric_name(args), "value": gbit, "unit": "Gbit/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / max(1, args.steps) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args, 1),
@@ -290,7 +294,7 @@ def ours_arm(args, rank, world, local_rank):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args), "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
             "clocks": clocks,
