@@ -355,16 +355,18 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
     h.acc_base = acc_base;
     h.n_acc = n_acc;
     h.srow_base = srow_base;
+    // Layout: the fixed-size tables first, at offsets that depend only on the sticky word count, so that the kernel
+    // addresses them with immediates: mask | cmap | sdesc | tab | t2 | tl2 | memb
     uint32_t off = 0;
+    h.off_mask = off;  off += 256u * 32u * (uint32_t)W;
+    h.off_cmap = off;  off += 512;
+    h.off_sdesc = off; off += nsb * 4;
     h.off_tab = off;   off = align16(off + (uint32_t)tab.size() * 4);
-    h.off_mask = off;  off = align16(off + (uint32_t)mask.size());
-    h.off_memb = off;  off = align16(off + (uint32_t)memb.size() * 4);
-    h.off_sdesc = off; off = align16(off + (uint32_t)sdesc.size() * 4);
     h.accel = accel ? 1u : 0u;
     h.nc2 = nc2;
-    h.off_cmap = off;  off = align16(off + 512);
     h.off_t2 = off;    off = align16(off + (uint32_t)t2.size() * 2);
     h.off_tl2 = off;   off = align16(off + (uint32_t)std::max<size_t>(8, tl2.size()) * 2);
+    h.off_memb = off;  off = align16(off + (uint32_t)memb.size() * 4);
     h.blob_bytes = off;
     if (img.why_not.empty() && off > opt.max_bytes) img.why_not = "tables need " + std::to_string(off) + " bytes of shared memory (limit " + std::to_string(opt.max_bytes) + ")";
     img.blob.assign(off, 0);

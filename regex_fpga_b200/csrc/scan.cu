@@ -147,8 +147,10 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
 
     // 32-bit shared-window addresses of the staged tables and of this lane's ring
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t tab_s = sbase + h.off_tab, mask_s = sbase + h.off_mask, memb_s = sbase + h.off_memb;
-    const uint32_t sdesc_s = sbase + h.off_sdesc, cmap_s = sbase + h.off_cmap, t2_s = sbase + h.off_t2, tl2_s = sbase + h.off_tl2;
+    // fixed-size tables sit at offsets that depend only on W (image.cpp): immediates in the load instructions
+    constexpr uint32_t OFF_CMAP = 256u * 32u * W, OFF_SDESC = OFF_CMAP + 512u, OFF_TAB = OFF_SDESC + 64u * W * 4u;
+    const uint32_t mask_s = sbase, cmap_s = sbase + OFF_CMAP, sdesc_s = sbase + OFF_SDESC, tab_s = sbase + OFF_TAB;
+    const uint32_t t2_s = sbase + h.off_t2, tl2_s = sbase + h.off_tl2, memb_s = sbase + h.off_memb;
     const uint32_t lb = sbase + h.blob_bytes + threadIdx.x * 2;   // ring entry at byte offset o: lb + o; bank-conflict free
     const uint32_t gbase = h.gbase, nsb = h.nsb, hmul = h.hash_mul, hsh = h.hash_shift;
     const uint32_t nbm = (1u << h.bucket_bits) - 1u;
@@ -176,6 +178,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;            // firing sticky bits not yet expanded
     uint32_t idx = 0;
     bool have = false, pend = false, walking = false, ovf = false;
+    bool firing = false;                                // (i0 | i1 | i2 | i3) != 0
 
     bool done = false;
     for (;;) {
@@ -291,9 +294,10 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                         P0 &= (uint64_t)kk.x | ((uint64_t)kk.y << 32);
                         P1 &= (uint64_t)kk.z | ((uint64_t)kk.w << 32);
                     }
+                    firing = (i0 | i1 | i2 | i3) != 0;
                 }
             }
-            pend = x != NONE || rp != re || (i0 | i1 | i2 | i3) != 0;
+            pend = x != NONE || rp != re || firing;
         }
         if (done) break;
 #pragma unroll 1
@@ -320,6 +324,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     else if (i1) { wsel = i1; wbase = 32; i1 &= i1 - 1; }
                     else if (i2) { wsel = i2; wbase = 64; i2 &= i2 - 1; }
                     else { wsel = i3; wbase = 96; i3 &= i3 - 1; }
+                    firing = (i0 | i1 | i2 | i3) != 0;
                     const uint32_t d = lds32(sdesc_s + (wbase + (uint32_t)__ffs((int)wsel) - 1u) * 4);
                     idx = (d & 0xFFFFu) + (hf & (d >> 16));
                     look = true;
@@ -353,7 +358,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     }
                 }
             }
-            pend = walking || x != NONE || rp != re || (i0 | i1 | i2 | i3) != 0;
+            pend = walking || x != NONE || rp != re || firing;
         }
     }
 }
