@@ -288,7 +288,8 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
     }
 
     // ---- two-symbol start table -------------------------------------------------------------------------
-    std::vector<uint16_t> cmap(256, 0), t2(1, 0xFFFF), tl2;
+    std::vector<uint32_t> cmap(256, 0);                       // per symbol: cls1 | cls2 << 8 | h(c) << 16
+    std::vector<uint16_t> t2(1, 0xFFFF), tl2;
     uint32_t nc1 = 1, nc2 = 1;
     if (accel) {
         std::map<std::vector<uint32_t>, uint32_t> c1id, c2id;
@@ -326,9 +327,11 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
                     t2[i * nc2 + j] = (uint16_t)(0x8000u | tl2.size());
                     for (size_t q = 0; q < tg.size(); q++) tl2.push_back((uint16_t)(tg[q] | (q + 1 < tg.size() ? 0x8000u : 0u)));
                 }
-            for (uint32_t c = 0; c < 256; c++) cmap[c] = (uint16_t)(cls1[c] | (cls2[c] << 8));
+            for (uint32_t c = 0; c < 256; c++) cmap[c] = cls1[c] | (cls2[c] << 8);
         }
     }
+
+    for (uint32_t c = 0; c < 256; c++) cmap[c] = (cmap[c] & 0xFFFFu) | (hfull(c, best_mul, best_sh) << 16);
 
     // ---- class membership bitmaps ---------------------------------------------------------------------
     std::vector<uint32_t> memb(std::max<size_t>(1, set_id.size()) * 8, 0);
@@ -359,7 +362,7 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
     // addresses them with immediates: mask | cmap | sdesc | tab | t2 | tl2 | memb
     uint32_t off = 0;
     h.off_mask = off;  off += 256u * 32u * (uint32_t)W;
-    h.off_cmap = off;  off += 512;
+    h.off_cmap = off;  off += 1024;
     h.off_sdesc = off; off += nsb * 4;
     h.off_tab = off;   off = align16(off + (uint32_t)tab.size() * 4);
     h.accel = accel ? 1u : 0u;
@@ -374,7 +377,7 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
     std::memcpy(&img.blob[h.off_mask], mask.data(), mask.size());
     std::memcpy(&img.blob[h.off_memb], memb.data(), memb.size() * 4);
     std::memcpy(&img.blob[h.off_sdesc], sdesc.data(), sdesc.size() * 4);
-    std::memcpy(&img.blob[h.off_cmap], cmap.data(), 512);
+    std::memcpy(&img.blob[h.off_cmap], cmap.data(), 1024);
     std::memcpy(&img.blob[h.off_t2], t2.data(), t2.size() * 2);
     if (!tl2.empty()) std::memcpy(&img.blob[h.off_tl2], tl2.data(), tl2.size() * 2);
 
@@ -425,7 +428,7 @@ void image_successors(const Image &img, uint32_t s, uint32_t c, std::vector<uint
         if (K[id >> 6] & bit) ids.push_back(id);
         if (M[id >> 6] & bit) { idx = (sdesc[id] & 0xFFFFu) + (hf & (sdesc[id] >> 16)); walk = true; }
         if (h.accel && id == 0) {   // targets reached only through the two-symbol table (checked in image_verify)
-            const uint16_t *cmap = reinterpret_cast<const uint16_t *>(&img.blob[h.off_cmap]);
+            const uint32_t *cmap = reinterpret_cast<const uint32_t *>(&img.blob[h.off_cmap]);
             for (uint32_t X : img.virt_of_cls1[cmap[c] & 0xFF]) ids.push_back(img.id_of_orig[X]);
         }
     } else if (id - h.acc_base < h.n_acc) {
@@ -474,7 +477,7 @@ int image_verify(const Nfa &nfa, const Image &img, std::string &err) {
     }
     if (img.h.accel) {   // T2[cls1(c1)][cls2(c2)] == successors on c2 of the virtual targets of A on c1
         const ImageHeader &h = img.h;
-        const uint16_t *cmap = reinterpret_cast<const uint16_t *>(&img.blob[h.off_cmap]);
+        const uint32_t *cmap = reinterpret_cast<const uint32_t *>(&img.blob[h.off_cmap]);
         const uint16_t *t2 = reinterpret_cast<const uint16_t *>(&img.blob[h.off_t2]);
         const uint16_t *tl2 = reinterpret_cast<const uint16_t *>(&img.blob[h.off_tl2]);
         for (uint32_t c1 = 0; c1 < 256; c1++) {
@@ -488,7 +491,7 @@ int image_verify(const Nfa &nfa, const Image &img, std::string &err) {
                 std::sort(want.begin(), want.end());
                 want.erase(std::unique(want.begin(), want.end()), want.end());
                 got.clear();
-                const uint32_t x = t2[(cmap[c1] & 0xFF) * h.nc2 + (cmap[c2] >> 8)];
+                const uint32_t x = t2[(cmap[c1] & 0xFF) * h.nc2 + ((cmap[c2] >> 8) & 0xFF)];
                 if (x != 0xFFFF) {
                     if (x < 0x8000) got.push_back(img.orig_of_id[x]);
                     else for (uint32_t q = x & 0x7FFF;; q++) { got.push_back(img.orig_of_id[tl2[q] & 0x7FFF]); if (!(tl2[q] & 0x8000)) break; }

@@ -148,11 +148,11 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     // 32-bit shared-window addresses of the staged tables and of this lane's ring
     const uint32_t sbase = smem_u32(smem);
     // fixed-size tables sit at offsets that depend only on W (image.cpp): immediates in the load instructions
-    constexpr uint32_t OFF_CMAP = 256u * 32u * W, OFF_SDESC = OFF_CMAP + 512u, OFF_TAB = OFF_SDESC + 64u * W * 4u;
+    constexpr uint32_t OFF_CMAP = 256u * 32u * W, OFF_SDESC = OFF_CMAP + 1024u, OFF_TAB = OFF_SDESC + 64u * W * 4u;
     const uint32_t mask_s = sbase, cmap_s = sbase + OFF_CMAP, sdesc_s = sbase + OFF_SDESC, tab_s = sbase + OFF_TAB;
     const uint32_t t2_s = sbase + h.off_t2, tl2_s = sbase + h.off_tl2, memb_s = sbase + h.off_memb;
     const uint32_t lb = sbase + h.blob_bytes + threadIdx.x * 2;   // ring entry at byte offset o: lb + o; bank-conflict free
-    const uint32_t gbase = h.gbase, nsb = h.nsb, hmul = h.hash_mul, hsh = h.hash_shift;
+    const uint32_t gbase = h.gbase, nsb = h.nsb;
     const uint32_t nbm = (1u << h.bucket_bits) - 1u;
     const uint32_t acc_base = h.acc_base, n_acc = h.n_acc, nc2 = h.nc2;
     const bool accel = h.accel != 0;
@@ -264,12 +264,12 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             c = b0 & 0xFFu;
             b0 = __funnelshift_r(b0, b1, 8); b1 = __funnelshift_r(b1, b2, 8); b2 = __funnelshift_r(b2, b3, 8); b3 >>= 8;
             bufn--;
-            hf = ((c * hmul) >> hsh) & 0xFFu;           // symbol hash; a row uses its low bits
+            const uint32_t cm = lds32(cmap_s + c * 4);  // per-symbol descriptor: cls1 | cls2 << 8 | hash << 16
+            hf = cm >> 16;                              // symbol hash; a row uses its low bits
             hc = hf & nbm;
             // two-symbol start table: successors of the never-materialised targets of state A
             if (accel) {
-                const uint32_t cm = lds16(cmap_s + c * 2);
-                x = lds16(t2_s + (pcls * nc2 + (cm >> 8)) * 2);
+                x = lds16(t2_s + (pcls * nc2 + ((cm >> 8) & 0xFFu)) * 2);
                 pcls = (P0 & 1ull) ? (cm & 0xFFu) : 0u;
             }
             // sticky states: survivors P & K[c]; those in P & M[c] fire their rows

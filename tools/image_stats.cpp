@@ -44,7 +44,7 @@ int main(int argc, char **argv) {
         Stats &s = st[j & 1];
         uint64_t P[2] = {0, 0};
         uint32_t pcls = 0;
-        const uint16_t *cmap = (const uint16_t *)&img.blob[h.off_cmap], *t2 = (const uint16_t *)&img.blob[h.off_t2], *tl2 = (const uint16_t *)&img.blob[h.off_tl2];
+        const uint32_t *cmap = (const uint32_t *)&img.blob[h.off_cmap]; const uint16_t *t2 = (const uint16_t *)&img.blob[h.off_t2], *tl2 = (const uint16_t *)&img.blob[h.off_tl2];
         std::vector<uint32_t> cur, nxt;
         if (h.start_id < h.nsb) P[h.start_id >> 6] |= 1ull << (h.start_id & 63); else cur.push_back(h.start_id);
         for (uint32_t k = 0; k < L; k++) {
@@ -65,7 +65,7 @@ int main(int argc, char **argv) {
                 }
             };
             if (h.accel) {
-                uint32_t cm = cmap[c], x = t2[pcls * h.nc2 + (cm >> 8)];
+                uint32_t cm = cmap[c], x = t2[pcls * h.nc2 + ((cm >> 8) & 0xFF)];
                 pcls = (P[0] & 1) ? (cm & 0xFF) : 0;
                 if (x != 0xFFFF) { s.t2hits++; if (x < 0x8000) push(x); else for (uint32_t q = x & 0x7FFF;; q++) { push(tl2[q] & 0x7FFF); if (!(tl2[q] & 0x8000)) break; } }
             }
