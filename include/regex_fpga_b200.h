@@ -63,7 +63,8 @@ typedef struct rfb_nfa_info {
     uint32_t n_slots;         /* entries of the edge table */
     uint32_t n_class_sets;    /* distinct symbol classes with more than two members */
     uint32_t bucket_bits;     /* log2 of buckets per branching state */
-    uint32_t reserved;
+    uint32_t n_parts;         /* > 1: the NFA is scanned as several independent groups of connected components,
+                                 each with tables that fit one SM (image_* fields describe the first) */
 } rfb_nfa_info;
 
 /* A batch of independent byte streams.  Stream s occupies bytes

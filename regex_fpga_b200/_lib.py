@@ -13,7 +13,7 @@ class rfb_match(C.Structure):
 class rfb_nfa_info(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in (
         "n_states", "n_transitions", "n_accepting", "n_entries", "image_ok", "image_bytes", "n_sticky",
-        "sticky_words", "n_slots", "n_class_sets", "bucket_bits", "reserved")]
+        "sticky_words", "n_slots", "n_class_sets", "bucket_bits", "n_parts")]
 
 
 class rfb_batch(C.Structure):

@@ -37,18 +37,31 @@ struct rfb_ctx {
     std::string err;
 };
 
-struct rfb_nfa {
-    rfb_ctx *ctx = nullptr;
-    int device = 0;                    // copy of ctx->device: the context may be destroyed first
-    Nfa host;
+// One independently scannable piece of an NFA: the whole NFA, or one group of its connected components.
+struct Part {
+    Nfa sub;
     Image img;
     Ecsr ecsr;
+    std::vector<uint32_t> to_orig;     // sub state id -> reference state id (empty: identity)
     NfaDev dev{};
     uint32_t *d_entries = nullptr;
     uint32_t *d_eptr = nullptr; unsigned long long *d_erec = nullptr; uint32_t *d_emembs = nullptr;
     uint8_t *d_blob = nullptr;
-    uint32_t *d_orig = nullptr;
+    uint32_t *d_orig = nullptr, *d_map = nullptr;
     uint32_t *d_idof = nullptr, *d_virt_ptr = nullptr, *d_virt_ids = nullptr;
+    void release() {
+        cudaFree(d_entries); cudaFree(d_eptr); cudaFree(d_erec); cudaFree(d_emembs); cudaFree(d_blob);
+        cudaFree(d_orig); cudaFree(d_map); cudaFree(d_idof); cudaFree(d_virt_ptr); cudaFree(d_virt_ids);
+    }
+};
+
+struct rfb_nfa {
+    rfb_ctx *ctx = nullptr;
+    int device = 0;                    // copy of ctx->device: the context may be destroyed first
+    Nfa host;                          // the NFA as loaded
+    std::vector<Part> parts;           // >= 1; several when the tables of the whole NFA do not fit one SM
+    NfaDev full{};                     // raw CSR of the whole NFA on the device (cycle model)
+    uint32_t *d_full = nullptr;
     uint32_t *d_state_in = nullptr, *d_state_out = nullptr; size_t d_state_cap_words = 0;   // rfb_scan staging
 };
 
@@ -90,6 +103,7 @@ static void fill_info(const Nfa &host, const Image &img, rfb_nfa_info *info) {
     info->n_slots = img.h.n_slots;
     info->n_class_sets = img.h.n_sets;
     info->bucket_bits = img.h.bucket_bits;
+    info->n_parts = 1;
 }
 
 static ImageOptions default_image_options() {
@@ -167,6 +181,46 @@ void rfb_ctx_destroy(rfb_ctx *ctx) {
 }
 
 // ---- transition memory ---------------------------------------------------------------------------
+// builds the device copy of one part: edge-grouped CSR always, execution image when it fits
+static int upload_part(rfb_ctx *ctx, Part &p, std::string &err) {
+    cudaError_t e;
+    int rc = ecsr_build(p.sub, p.ecsr, err);
+    if (rc) return rc;
+    const Nfa &h = p.sub;
+    const Ecsr &ec = p.ecsr;
+#define UP(ptr, vec, T)                                                                                             \
+    if ((e = cudaMalloc(reinterpret_cast<void **>(&ptr), std::max<size_t>(1, (vec).size()) * sizeof(T))) != cudaSuccess || \
+        (e = cudaMemcpy(ptr, (vec).data(), (vec).size() * sizeof(T), cudaMemcpyHostToDevice)) != cudaSuccess)         \
+        return cuda_fail(ctx, e, "upload NFA tables")
+    UP(p.d_entries, h.entries, uint32_t);
+    UP(p.d_eptr, ec.eptr, uint32_t);
+    UP(p.d_erec, ec.erec, unsigned long long);
+    UP(p.d_emembs, ec.memb, uint32_t);
+    p.dev.n_states = h.n_states;
+    p.dev.row_ptr = p.d_entries;
+    p.dev.trans = p.d_entries + h.n_states + 1;
+    p.dev.eptr = p.d_eptr; p.dev.erec = p.d_erec; p.dev.emembs = p.d_emembs;
+    if (!p.to_orig.empty()) { UP(p.d_map, p.to_orig, uint32_t); p.dev.state_map = p.d_map; }
+    if (p.img.ok) {
+        const Image &im = p.img;
+        std::vector<uint32_t> orig = im.orig_of_id;                     // internal id -> REFERENCE state id
+        if (!p.to_orig.empty()) for (auto &o : orig) if (o != 0xFFFFFFFFu) o = p.to_orig[o];
+        std::vector<uint32_t> vptr(1, 0), vids;
+        for (const auto &v : im.virt_of_cls1) { vids.insert(vids.end(), v.begin(), v.end()); vptr.push_back((uint32_t)vids.size()); }
+        if (vptr.size() < 2) vptr.push_back(0);
+        UP(p.d_blob, im.blob, uint8_t);
+        UP(p.d_orig, orig, uint32_t);
+        UP(p.d_idof, im.id_of_orig, uint32_t);
+        UP(p.d_virt_ptr, vptr, uint32_t);
+        UP(p.d_virt_ids, vids, uint32_t);
+        p.dev.blob = p.d_blob; p.dev.orig_of_id = p.d_orig;
+        p.dev.id_of_orig = p.d_idof; p.dev.virt_ptr = p.d_virt_ptr; p.dev.virt_ids = p.d_virt_ids;
+        p.dev.h = im.h;
+    }
+#undef UP
+    return RFB_OK;
+}
+
 int rfb_nfa_from_entries(rfb_ctx *ctx, const uint32_t *entries, size_t n_entries, int64_t n_states, rfb_nfa **out) {
     if (!ctx || !out || !entries) return fail(ctx, RFB_E_INVALID, "NULL argument");
     *out = nullptr;
@@ -177,63 +231,53 @@ int rfb_nfa_from_entries(rfb_ctx *ctx, const uint32_t *entries, size_t n_entries
     std::string err;
     int rc = nfa_from_entries(entries, n_entries, n_states, nfa->host, err);
     if (rc) { delete nfa; return fail(ctx, rc, err); }
-    ImageOptions opt = default_image_options();
-    rc = image_build(nfa->host, opt, nfa->img, err);
-    if (rc) { delete nfa; return fail(ctx, rc, err); }
-    rc = ecsr_build(nfa->host, nfa->ecsr, err);
-    if (rc) { delete nfa; return fail(ctx, rc, err); }
-
+    const ImageOptions opt = default_image_options();
     cudaSetDevice(ctx->device);
-    const Nfa &h = nfa->host;
-    cudaError_t e;
-    if ((e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_entries), h.entries.size() * 4)) != cudaSuccess ||
-        (e = cudaMemcpy(nfa->d_entries, h.entries.data(), h.entries.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
-        rfb_nfa_destroy(nfa);
-        return cuda_fail(ctx, e, "upload CSR");
-    }
-    {
-        const Ecsr &ec = nfa->ecsr;
-        if ((e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_eptr), ec.eptr.size() * 4)) != cudaSuccess ||
-            (e = cudaMemcpy(nfa->d_eptr, ec.eptr.data(), ec.eptr.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
-            (e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_erec), std::max<size_t>(1, ec.erec.size()) * 8)) != cudaSuccess ||
-            (e = cudaMemcpy(nfa->d_erec, ec.erec.data(), ec.erec.size() * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
-            (e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_emembs), ec.memb.size() * 4)) != cudaSuccess ||
-            (e = cudaMemcpy(nfa->d_emembs, ec.memb.data(), ec.memb.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
-            rfb_nfa_destroy(nfa);
-            return cuda_fail(ctx, e, "upload edge-grouped CSR");
-        }
-        nfa->dev.eptr = nfa->d_eptr; nfa->dev.erec = nfa->d_erec; nfa->dev.emembs = nfa->d_emembs;
-    }
-    nfa->dev.n_states = h.n_states;
-    nfa->dev.row_ptr = nfa->d_entries;
-    nfa->dev.trans = nfa->d_entries + h.n_states + 1;
-    if (nfa->img.ok) {
-        const Image &im = nfa->img;
-        if ((e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_blob), im.blob.size())) != cudaSuccess ||
-            (e = cudaMemcpy(nfa->d_blob, im.blob.data(), im.blob.size(), cudaMemcpyHostToDevice)) != cudaSuccess ||
-            (e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_orig), im.orig_of_id.size() * 4)) != cudaSuccess ||
-            (e = cudaMemcpy(nfa->d_orig, im.orig_of_id.data(), im.orig_of_id.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
-            rfb_nfa_destroy(nfa);
-            return cuda_fail(ctx, e, "upload execution image");
-        }
-        {   // id maps for resumable scans
-            std::vector<uint32_t> vptr(1, 0), vids;
-            for (const auto &v : im.virt_of_cls1) { vids.insert(vids.end(), v.begin(), v.end()); vptr.push_back((uint32_t)vids.size()); }
-            if (vptr.size() < 2) vptr.push_back(0);
-            if ((e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_idof), im.id_of_orig.size() * 4)) != cudaSuccess ||
-                (e = cudaMemcpy(nfa->d_idof, im.id_of_orig.data(), im.id_of_orig.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
-                (e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_virt_ptr), vptr.size() * 4)) != cudaSuccess ||
-                (e = cudaMemcpy(nfa->d_virt_ptr, vptr.data(), vptr.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess ||
-                (e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_virt_ids), std::max<size_t>(1, vids.size()) * 4)) != cudaSuccess ||
-                (e = cudaMemcpy(nfa->d_virt_ids, vids.data(), vids.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
-                rfb_nfa_destroy(nfa);
-                return cuda_fail(ctx, e, "upload id maps");
+
+    // the whole NFA as one part if its tables fit one SM; otherwise groups of connected components, each with
+    // tables that fit; if it cannot be split, one part served by the general kernel
+    nfa->parts.resize(1);
+    nfa->parts[0].sub = nfa->host;
+    rc = image_build(nfa->host, opt, nfa->parts[0].img, err);
+    if (rc) { delete nfa; return fail(ctx, rc, err); }
+    if (!nfa->parts[0].img.ok && !std::getenv("RFB_NO_SPLIT")) {
+        // Prefer the coarsest cut whose parts all get full-quality tables (>= 8 buckets per branching state, every
+        // self-looping state in the mask): such a part runs at the speed of a small NFA, and a part that misses
+        // either costs far more than one extra pass over the batch.  Otherwise the coarsest cut that fits at all.
+        std::vector<Part> fallback;
+        for (uint32_t limit = 24000; limit >= 1500; limit /= 2) {
+            std::vector<std::vector<uint32_t>> groups;
+            nfa_components(nfa->host, limit, groups);
+            if (groups.empty()) break;
+            std::vector<Part> parts(groups.size());
+            bool all_ok = true, all_good = true;
+            for (size_t g = 0; g < groups.size() && rc == RFB_OK; g++) {
+                rc = nfa_extract(nfa->host, groups[g], parts[g].sub, parts[g].to_orig, err);
+                if (rc == RFB_OK) rc = image_build(parts[g].sub, opt, parts[g].img, err);
+                all_ok = all_ok && parts[g].img.ok;
+                all_good = all_good && parts[g].img.ok && parts[g].img.h.bucket_bits >= 3 && parts[g].img.n_sticky_dropped == 0;
             }
-            nfa->dev.id_of_orig = nfa->d_idof; nfa->dev.virt_ptr = nfa->d_virt_ptr; nfa->dev.virt_ids = nfa->d_virt_ids;
+            if (rc) { delete nfa; return fail(ctx, rc, err); }
+            if (all_good) { nfa->parts.swap(parts); fallback.clear(); break; }
+            if (all_ok && fallback.empty()) fallback.swap(parts);
         }
-        nfa->dev.blob = nfa->d_blob;
-        nfa->dev.orig_of_id = nfa->d_orig;
-        nfa->dev.h = im.h;
+        if (!fallback.empty()) nfa->parts.swap(fallback);
+    }
+    for (Part &p : nfa->parts) {
+        rc = upload_part(ctx, p, err);
+        if (rc) { rfb_nfa_destroy(nfa); return rc == RFB_E_CUDA ? rc : fail(ctx, rc, err); }
+    }
+    if (nfa->parts.size() == 1) nfa->full = nfa->parts[0].dev;
+    else {
+        cudaError_t e;
+        if ((e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_full), nfa->host.entries.size() * 4)) != cudaSuccess ||
+            (e = cudaMemcpy(nfa->d_full, nfa->host.entries.data(), nfa->host.entries.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+            rfb_nfa_destroy(nfa);
+            return cuda_fail(ctx, e, "upload CSR");
+        }
+        nfa->full.n_states = nfa->host.n_states;
+        nfa->full.row_ptr = nfa->d_full;
+        nfa->full.trans = nfa->d_full + nfa->host.n_states + 1;
     }
     *out = nfa;
     return RFB_OK;
@@ -251,16 +295,18 @@ int rfb_nfa_load_coe(rfb_ctx *ctx, const char *path, int64_t n_states, rfb_nfa *
 void rfb_nfa_destroy(rfb_nfa *nfa) {
     if (!nfa) return;
     cudaSetDevice(nfa->device);
-    cudaFree(nfa->d_entries); cudaFree(nfa->d_blob); cudaFree(nfa->d_orig);
-    cudaFree(nfa->d_eptr); cudaFree(nfa->d_erec); cudaFree(nfa->d_emembs);
-    cudaFree(nfa->d_idof); cudaFree(nfa->d_virt_ptr); cudaFree(nfa->d_virt_ids);
-    cudaFree(nfa->d_state_in); cudaFree(nfa->d_state_out);
+    for (Part &p : nfa->parts) p.release();
+    cudaFree(nfa->d_full); cudaFree(nfa->d_state_in); cudaFree(nfa->d_state_out);
     delete nfa;
 }
 
 int rfb_nfa_get_info(const rfb_nfa *nfa, rfb_nfa_info *info) {
     if (!nfa || !info) return fail(nullptr, RFB_E_INVALID, "NULL argument");
-    fill_info(nfa->host, nfa->img, info);
+    fill_info(nfa->host, nfa->parts[0].img, info);
+    bool all_ok = true;
+    for (const Part &p : nfa->parts) all_ok = all_ok && p.img.ok;
+    info->image_ok = all_ok ? 1u : 0u;
+    info->n_parts = (uint32_t)nfa->parts.size();
     return RFB_OK;
 }
 
@@ -385,12 +431,21 @@ static int enqueue_kernels(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b,
     od.records = res->records; od.capacity = res->records ? res->record_capacity : 0;
     od.g = ctx->g; od.rescan = ctx->rescan;
     if (b->n_streams) {
-        const bool lane = nfa->img.ok && !(flags & RFB_SCAN_FORCE_WARP);
-        if (lane) {
-            CU(ctx, launch_scan_lane(nfa->dev, bd, od, ctx->n_sms, st)); (*launches)++;
-            CU(ctx, launch_scan_warp(nfa->dev, bd, od, true, ctx->n_sms, st)); (*launches)++;
-        } else {
-            CU(ctx, launch_scan_warp(nfa->dev, bd, od, false, ctx->n_sms, st)); (*launches)++;
+        bool first = true;
+        for (const Part &p : nfa->parts) {   // one pass over the batch per part; reports of different parts are disjoint
+            if (!first) {
+                CU(ctx, cudaMemsetAsync(&ctx->g->next_stream, 0, 3 * sizeof(unsigned int), st));
+                bd.chunk_streams = 0;        // the batch is resident once the first pass has consumed it
+            }
+            bd.count_symbols = first ? 1u : 0u;
+            const bool lane = p.img.ok && !(flags & RFB_SCAN_FORCE_WARP);
+            if (lane) {
+                CU(ctx, launch_scan_lane(p.dev, bd, od, ctx->n_sms, st)); (*launches)++;
+                CU(ctx, launch_scan_warp(p.dev, bd, od, true, ctx->n_sms, st)); (*launches)++;
+            } else {
+                CU(ctx, launch_scan_warp(p.dev, bd, od, false, ctx->n_sms, st)); (*launches)++;
+            }
+            first = false;
         }
     }
     return RFB_OK;
@@ -402,6 +457,7 @@ int rfb_scan_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
     int rc = check_batch(ctx, b, false);
     if (rc) return rc;
     if (flags & RFB_SCAN_SORT_RECORDS) return fail(ctx, RFB_E_UNSUPPORTED, "RFB_SCAN_SORT_RECORDS is only available through rfb_scan");
+    if ((b->state_in || b->state_out) && nfa->parts.size() > 1) return fail(ctx, RFB_E_UNSUPPORTED, "resumable scans are not available for an NFA that is scanned in several parts");
     cudaSetDevice(ctx->device);
     (void)cudaGetLastError();   // a stale error of an unrelated earlier call must not be blamed on this launch
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
@@ -434,6 +490,7 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     if (rc) return rc;
     cudaSetDevice(ctx->device);
     (void)cudaGetLastError();
+    if ((b->state_in || b->state_out) && nfa->parts.size() > 1) return fail(ctx, RFB_E_UNSUPPORTED, "resumable scans are not available for an NFA that is scanned in several parts");
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
     const size_t padded = ((size_t)b->data_bytes + 15) / 16 * 16 + 16;
     CU(ctx, ensure(ctx->d_data, ctx->d_data_cap, padded));
@@ -480,7 +537,7 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     // overlaps the H2D transfer at full occupancy.  Other batches (explicit offsets, general kernel only) wait
     // for the whole copy.
     uint32_t launches = 0;
-    const bool lane_path = nfa->img.ok && !(flags & RFB_SCAN_FORCE_WARP);
+    const bool lane_path = nfa->parts[0].img.ok && !(flags & RFB_SCAN_FORCE_WARP);
     uint64_t n_chunks = 1;
     if (lane_path && !b->offsets && b->n_streams >= 64 && b->stride > 0)
         n_chunks = std::min<uint64_t>(16, std::max<uint64_t>(1, b->data_bytes / (64ull << 20)));
@@ -558,7 +615,7 @@ int rfb_fpga_cycles(rfb_ctx *ctx, const rfb_nfa *nfa, const uint8_t *lo, const u
         (e = cudaMemcpyAsync(d_cost, cost.data(), cost.size() * 4, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
         (e = cudaMemcpyAsync(d_tr, lo, trace_entries, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
         (e = cudaMemcpyAsync(d_tr + trace_entries, hi, trace_entries, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess ||
-        (e = launch_tb_cycles(nfa->dev, d_cost, d_tr, d_tr + trace_entries, n_steps, d_total, ctx->stream)) != cudaSuccess ||
+        (e = launch_tb_cycles(nfa->full, d_cost, d_tr, d_tr + trace_entries, n_steps, d_total, ctx->stream)) != cudaSuccess ||
         (e = cudaMemcpyAsync(cycles, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess ||
         (e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess)
         rc = cuda_fail(ctx, e, "rfb_fpga_cycles");

@@ -30,6 +30,7 @@ struct BatchDev {
     unsigned int chunk_streams;
     const unsigned int *ready;
     // resumable scans: per-stream active sets in / out (original state ids), stride 1 + state_cap words
+    unsigned int count_symbols;  // ragged batches: add the stream lengths to n_symbols (first part of a multi-part NFA only)
     unsigned int pos_base;
     unsigned int state_cap;
     const unsigned int *state_in;
@@ -52,6 +53,7 @@ struct NfaDev {
     const uint32_t *eptr;        // [n_states + 1]
     const unsigned long long *erec;   // [n_edges]
     const uint32_t *emembs;      // [n_sets * 8]
+    const uint32_t *state_map;   // general kernel: state id of this (sub-)NFA -> reference state id; NULL = identity
     // execution image
     const uint8_t *blob;         // ImageHeader::blob_bytes bytes, 16-byte aligned
     const uint32_t *orig_of_id;  // [n_slots]

@@ -33,6 +33,16 @@ struct Nfa {
 // Validates and adopts an image.  n_states < 0: auto-detect.
 int nfa_from_entries(const uint32_t *entries, size_t n, int64_t n_states, Nfa &out, std::string &err);
 
+// ---- parts.cpp --------------------------------------------------------------------------------
+// An NFA whose tables do not fit one SM's shared memory is cut along its connected components (the start state 0,
+// which nothing targets, is shared): the NFA step is a union over active states and no transition crosses
+// components, so scanning a stream against every part and merging the reports is exact.  BASELINE config 5
+// (7 x snort_16 behind one start state, 66 592 states) becomes 7 parts of 9 514 states.
+// groups[g] = sorted original ids (without state 0) of part g; empty result = cannot be split.
+void nfa_components(const Nfa &nfa, uint32_t max_states_per_part, std::vector<std::vector<uint32_t>> &groups);
+// sub-NFA of state 0 (row restricted to the part) + `states`; to_orig[i] = original id of sub state i
+int nfa_extract(const Nfa &nfa, const std::vector<uint32_t> &states, Nfa &sub, std::vector<uint32_t> &to_orig, std::string &err);
+
 // ---- ecsr.cpp ---------------------------------------------------------------------------------
 // Edge-grouped CSR for the general kernel: a state's transitions grouped by target, one 64-bit record per
 // (symbol-set -> target) edge instead of one entry per (symbol, target) pair.  A state that self-loops on all
@@ -87,6 +97,7 @@ struct Image {
     std::vector<uint32_t> orig_of_id;  // internal id -> original state id (0xFFFFFFFF: not a state)
     std::vector<uint32_t> id_of_orig;  // original state id -> internal id
     uint32_t n_sticky = 0;
+    uint32_t n_sticky_dropped = 0;                      // self-looping states that did not fit the mask (run as ordinary states)
     // accelerated sticky state (host-side description for the verifier)
     uint32_t accel_state = 0xFFFFFFFFu;                 // original id
     std::vector<std::vector<uint32_t>> virt_of_cls1;   // class of c1 -> virtual targets (original ids)

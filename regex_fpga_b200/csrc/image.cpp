@@ -86,7 +86,7 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
     int W = opt.sticky_words;
     if (W != 1 && W != 2) W = cand.size() <= 64 ? 1 : 2;
     const uint32_t nsb = 64u * (uint32_t)W;
-    if (cand.size() > nsb) cand.resize(nsb);
+    if (cand.size() > nsb) { img.n_sticky_dropped = (uint32_t)(cand.size() - nsb); cand.resize(nsb); }
     std::vector<int32_t> sticky_bit(N, -1);
     for (size_t b = 0; b < cand.size(); b++) sticky_bit[cand[b]] = (int32_t)b;
     img.n_sticky = (uint32_t)cand.size();

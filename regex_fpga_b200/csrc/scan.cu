@@ -214,7 +214,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                                     batch.state_out + (size_t)sid * (1u + batch.state_cap), batch.state_cap);
                 }
                 if (sid >= batch.n_streams) { done = true; break; }   // this lane is done
-                if (batch.steps) atomicAdd(&out.g->n_symbols, (unsigned long long)nsteps);
+                if (batch.steps && batch.count_symbols) atomicAdd(&out.g->n_symbols, (unsigned long long)nsteps);
                 if (batch.chunk_streams) {   // host path: wait until the H2D copy of this stream's chunk has landed
                     const unsigned int need = sid / batch.chunk_streams + 1u;
                     while (*reinterpret_cast<const volatile unsigned int *>(batch.ready) < need) __nanosleep(256);
@@ -402,6 +402,7 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
     const uint32_t *__restrict__ ep = nfa.eptr;
     const unsigned long long *__restrict__ er = nfa.erec;
     const uint32_t *__restrict__ em = nfa.emembs;
+    const uint32_t *__restrict__ smap = nfa.state_map;
 
     for (uint32_t w = lane; w < 2 * nw; w += 32) bits_cur[w] = 0;
     __syncwarp();
@@ -431,7 +432,7 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
             sid = item;
         }
         const uint32_t nsteps = batch.steps ? batch.steps[sid] : batch.n_steps;
-        if (!from_rescan && batch.steps && lane == 0) atomicAdd(&out.g->n_symbols, (unsigned long long)nsteps);
+        if (!from_rescan && batch.steps && batch.count_symbols && lane == 0) atomicAdd(&out.g->n_symbols, (unsigned long long)nsteps);
         const uint8_t *sp = stream_ptr(batch, sid);
 
         uint32_t ncur = 1;
@@ -450,7 +451,7 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
             // expand S_k through the edge-grouped rows: one active state per lane, its few edges serially
             auto expand = [&](uint32_t s) {
                 const uint32_t e0 = ep[s], e1 = ep[s + 1];
-                if (e0 == e1) { if (report) emit_match(out, sid + batch.stream_id_base, k + batch.pos_base, s); return; }   // FPGA.v:210-226
+                if (e0 == e1) { if (report) emit_match(out, sid + batch.stream_id_base, k + batch.pos_base, smap ? smap[s] : s); return; }   // FPGA.v:210-226
                 for (uint32_t j = e0; j < e1; j++) {
                     const unsigned long long r = er[j];
                     const uint32_t lo = (uint32_t)r;
@@ -464,7 +465,7 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
                 for (uint32_t i = 0; i < ncur; i++) {
                     const uint32_t s = list_cur[i];
                     const uint32_t e0 = ep[s], e1 = ep[s + 1];
-                    if (e0 == e1 && report && lane == 0) emit_match(out, sid + batch.stream_id_base, k + batch.pos_base, s);   // FPGA.v:210-226
+                    if (e0 == e1 && report && lane == 0) emit_match(out, sid + batch.stream_id_base, k + batch.pos_base, smap ? smap[s] : s);   // FPGA.v:210-226
                     for (uint32_t j = e0 + lane; j < e1; j += 32) {
                         const unsigned long long r = er[j];
                         const uint32_t lo = (uint32_t)r;

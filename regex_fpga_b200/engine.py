@@ -35,7 +35,7 @@ def _check(rc, ctx=None):
 
 
 def _info_dict(info):
-    return {n: int(getattr(info, n)) for n, _ in rfb_nfa_info._fields_ if n != "reserved"}
+    return {n: int(getattr(info, n)) for n, _ in rfb_nfa_info._fields_}
 
 
 # ---- host-only helpers (formats; no GPU) ---------------------------------------------------------

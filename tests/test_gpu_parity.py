@@ -302,23 +302,45 @@ def test_resume_with_more_states_than_the_ring_holds(gpu_ctx):
 
 def test_config5_replicated_large_nfa_adversarial(gpu_ctx, snort):
     """BASELINE config 5: 7 x snort_16 behind one start state (66 592 states, beyond the FPGA's own 16-bit
-    rd_address) with adversarial high-activity streams and hi-trace windows.  Too large for the 15-bit ids of
-    the lane kernel's tables, so this exercises the general warp kernel on a big NFA; bit-exact vs oracle B."""
+    rd_address) with adversarial high-activity streams and hi-trace windows.  The tables of the whole NFA do not fit
+    one SM, so the library cuts it along its connected components into 7 parts and scans the batch once per part
+    (lane kernel); FORCE_WARP runs the general kernel on the same parts.  Bit-exact vs oracle B on the FULL NFA."""
     E7, n7 = WL.replicate_nfa(snort.entries, snort.n_states, 7)
     assert n7 == 66592 and int(E7[n7]) == 558992
     nfa = gpu_ctx.nfa_from_entries(E7, n7)
-    assert nfa.info["image_ok"] == 0
+    assert nfa.info["n_parts"] == 7 and nfa.info["image_ok"] == 1
     adv = WL.make_adversarial_numpy(snort.entries, snort.n_states, snort.hi, 96)
     whi = WL.make_batch_numpy("whi", snort.lo, snort.hi, 96, 1500, 1536, seed=0x5EED0005)
     data = np.concatenate([adv, whi])
-    got = check_against_oracle(nfa, E7, n7, data, 1500, R.SCAN_SORT_RECORDS)
-    assert got.n_matches > 100
+    for _, flags in KERNELS:
+        got = check_against_oracle(nfa, E7, n7, data, 1500, flags)
+        assert got.n_matches > 100
     # every replica sees the same bytes, so a match on state s of replica 0 appears on all 7 replicas
     one = gpu_ctx.nfa_from_entries(snort.entries).scan(data, data.shape[0], n_steps=1500, stride=1536)
     assert got.n_matches == 7 * one.n_matches
     per = got.counts[1:].reshape(7, snort.n_states - 1)
     assert all(np.array_equal(per[0], per[r]) for r in range(1, 7))
     assert np.array_equal(per[0], one.counts[1:])
+    # ragged lengths: symbols are counted once, not once per part
+    steps = np.full(data.shape[0], 1500, np.uint32)
+    steps[::3] = 100
+    rag = nfa.scan(data, data.shape[0], stride=1536, steps=steps)
+    assert rag.n_symbols == int(steps.sum())
+    with pytest.raises(R.RfbError):                                  # resumable scans need a single-part NFA
+        nfa.scan(data, data.shape[0], n_steps=10, stride=1536, want_state=True)
+
+
+def test_unsplittable_large_nfa_uses_general_kernel(gpu_ctx):
+    """One connected component too large for the lane tables: a single part on the general kernel."""
+    n = 40000
+    rows = [[(1, 1)]] + [[(1, (s % (n - 1)) + 1), (2, ((s * 7) % (n - 1)) + 1)] for s in range(1, n - 1)] + [[]]
+    rows[5] = [(1, 6), (3, n - 1)]
+    E, ns = build_entries(rows)
+    nfa = gpu_ctx.nfa_from_entries(E, ns)
+    assert nfa.info["n_parts"] == 1 and nfa.info["image_ok"] == 0
+    rng = np.random.default_rng(9)
+    data = rng.choice(np.array([1, 1, 2, 3], np.uint8), size=(64, 120))
+    check_against_oracle(nfa, E, ns, data, 120, R.SCAN_SORT_RECORDS)
 
 
 def test_host_path_chunked_overlap_matches_device_path(gpu_ctx, snort):
