@@ -29,6 +29,8 @@ struct rfb_ctx {
     unsigned int *d_steps = nullptr; size_t d_steps_cap = 0;
     unsigned long long *d_counts = nullptr; size_t d_counts_cap = 0;
     rfb_match *d_records = nullptr; size_t d_records_cap = 0;
+    unsigned int *d_state_in = nullptr; size_t d_state_in_cap = 0;     // resumable scans: per-stream sets in / out
+    unsigned int *d_state_out = nullptr; size_t d_state_out_cap = 0;
     // state of the last enqueued scan (for rfb_scan_collect)
     cudaStream_t last_stream = nullptr;
     unsigned long long last_symbols = 0;
@@ -62,7 +64,6 @@ struct rfb_nfa {
     std::vector<Part> parts;           // >= 1; several when the tables of the whole NFA do not fit one SM
     NfaDev full{};                     // raw CSR of the whole NFA on the device (cycle model)
     uint32_t *d_full = nullptr;
-    uint32_t *d_state_in = nullptr, *d_state_out = nullptr; size_t d_state_cap_words = 0;   // rfb_scan staging
 };
 
 static int fail(rfb_ctx *ctx, int code, const std::string &msg) {
@@ -176,7 +177,7 @@ void rfb_ctx_destroy(rfb_ctx *ctx) {
     if (ctx->chunk_vals) cudaFreeHost(ctx->chunk_vals);
     cudaFree(ctx->rescan);
     cudaFree(ctx->d_data); cudaFree(ctx->d_offsets); cudaFree(ctx->d_steps);
-    cudaFree(ctx->d_counts); cudaFree(ctx->d_records);
+    cudaFree(ctx->d_counts); cudaFree(ctx->d_records); cudaFree(ctx->d_state_in); cudaFree(ctx->d_state_out);
     delete ctx;
 }
 
@@ -296,7 +297,7 @@ void rfb_nfa_destroy(rfb_nfa *nfa) {
     if (!nfa) return;
     cudaSetDevice(nfa->device);
     for (Part &p : nfa->parts) p.release();
-    cudaFree(nfa->d_full); cudaFree(nfa->d_state_in); cudaFree(nfa->d_state_out);
+    cudaFree(nfa->d_full);
     delete nfa;
 }
 
@@ -384,7 +385,7 @@ uint32_t rfb_tb_steps(uint32_t trace_entries) { return trace_entries ? trace_ent
 // ---- the scan ----------------------------------------------------------------------------------------
 static int check_batch(rfb_ctx *ctx, const rfb_batch *b, bool host) {
     if (!b) return fail(ctx, RFB_E_INVALID, "batch is NULL");
-    if (b->n_streams > 0xFFFFFFFFull) return fail(ctx, RFB_E_INVALID, "n_streams exceeds 2^32-1 (stream ids are 32-bit)");
+    if (b->n_streams > 0xFFF00000ull) return fail(ctx, RFB_E_INVALID, "n_streams exceeds 2^32 - 2^20 (stream ids and the fetch counter are 32-bit)");
     if (b->n_streams && !b->data && b->data_bytes) return fail(ctx, RFB_E_INVALID, "data is NULL");
     if ((b->state_in || b->state_out) && (b->state_cap == 0 || b->state_cap > 255)) return fail(ctx, RFB_E_INVALID, "state_cap must be 1..255 when state_in/state_out are used");
     if (host) {  // host pointers can be bounds-checked
@@ -508,15 +509,15 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
         db.steps = ctx->d_steps;
     }
     const size_t state_words = (size_t)b->n_streams * (1 + (size_t)b->state_cap);
-    rfb_nfa *mnfa = const_cast<rfb_nfa *>(nfa);   // staging buffers live with the NFA handle
-    if ((b->state_in || b->state_out) && mnfa->d_state_cap_words < state_words) {
-        cudaFree(mnfa->d_state_in); cudaFree(mnfa->d_state_out); mnfa->d_state_in = mnfa->d_state_out = nullptr; mnfa->d_state_cap_words = 0;
-        CU(ctx, cudaMalloc(reinterpret_cast<void **>(&mnfa->d_state_in), std::max<size_t>(16, state_words) * 4));
-        CU(ctx, cudaMalloc(reinterpret_cast<void **>(&mnfa->d_state_out), std::max<size_t>(16, state_words) * 4));
-        mnfa->d_state_cap_words = state_words;
+    if (b->state_in) {
+        CU(ctx, ensure(ctx->d_state_in, ctx->d_state_in_cap, state_words));
+        CU(ctx, cudaMemcpyAsync(ctx->d_state_in, b->state_in, state_words * 4, cudaMemcpyHostToDevice, st));
+        db.state_in = ctx->d_state_in;
     }
-    if (b->state_in) { CU(ctx, cudaMemcpyAsync(mnfa->d_state_in, b->state_in, state_words * 4, cudaMemcpyHostToDevice, st)); db.state_in = mnfa->d_state_in; }
-    if (b->state_out) db.state_out = mnfa->d_state_out;
+    if (b->state_out) {
+        CU(ctx, ensure(ctx->d_state_out, ctx->d_state_out_cap, state_words));
+        db.state_out = ctx->d_state_out;
+    }
     rfb_result dr = *res;
     const bool want_counts = res->counts && !(flags & RFB_SCAN_NO_COUNTS);
     if (want_counts) {
@@ -573,7 +574,7 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     if (rc) return rc;
     if (want_counts) CU(ctx, cudaMemcpyAsync(res->counts, ctx->d_counts, (size_t)nfa->host.n_states * 8, cudaMemcpyDeviceToHost, st));
     if (dr.n_records) CU(ctx, cudaMemcpyAsync(res->records, ctx->d_records, dr.n_records * sizeof(rfb_match), cudaMemcpyDeviceToHost, st));
-    if (b->state_out && state_words) CU(ctx, cudaMemcpyAsync(b->state_out, mnfa->d_state_out, state_words * 4, cudaMemcpyDeviceToHost, st));
+    if (b->state_out && state_words) CU(ctx, cudaMemcpyAsync(b->state_out, ctx->d_state_out, state_words * 4, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     res->n_matches = dr.n_matches; res->n_records = dr.n_records; res->n_dropped = dr.n_dropped;
     res->n_symbols = dr.n_symbols; res->n_rescanned = dr.n_rescanned; res->gpu_ms = dr.gpu_ms;

@@ -71,7 +71,8 @@ __device__ __forceinline__ void stage_image(uint8_t *dst, const uint8_t *src, ui
 // ring entries per stream: the largest of 64 / 32 / 16 that fits beside the image (a full ring hands the stream
 // to the general kernel, which is an order of magnitude slower, so capacity is worth the shared memory)
 int lane_ring_cap(const ImageHeader &h) {
-    for (int cap = 64; cap >= 16; cap >>= 1)
+    static const int max_cap = [] { const char *e = getenv("RFB_RING_CAP"); const int v = e ? atoi(e) : 64; return v >= 64 ? 64 : v >= 32 ? 32 : 16; }();
+    for (int cap = max_cap; cap >= 16; cap >>= 1)
         if ((size_t)h.blob_bytes + (size_t)cap * LANE_THREADS * 2 + 16 <= MAX_DYN_SMEM) return cap;
     return 0;
 }
