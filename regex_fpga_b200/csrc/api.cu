@@ -29,6 +29,8 @@ struct rfb_ctx {
     unsigned int *d_steps = nullptr; size_t d_steps_cap = 0;
     unsigned long long *d_counts = nullptr; size_t d_counts_cap = 0;
     rfb_match *d_records = nullptr; size_t d_records_cap = 0;
+    rfb_match *d_sort_tmp = nullptr; size_t d_sort_tmp_cap = 0;       // canonical ordering: ping-pong buffer + histograms
+    uint32_t *d_sort_hist = nullptr; size_t d_sort_hist_cap = 0;
     unsigned int *d_state_in = nullptr; size_t d_state_in_cap = 0;     // resumable scans: per-stream sets in / out
     unsigned int *d_state_out = nullptr; size_t d_state_out_cap = 0;
     // state of the last enqueued scan (for rfb_scan_collect)
@@ -178,6 +180,7 @@ void rfb_ctx_destroy(rfb_ctx *ctx) {
     cudaFree(ctx->rescan);
     cudaFree(ctx->d_data); cudaFree(ctx->d_offsets); cudaFree(ctx->d_steps);
     cudaFree(ctx->d_counts); cudaFree(ctx->d_records); cudaFree(ctx->d_state_in); cudaFree(ctx->d_state_out);
+    cudaFree(ctx->d_sort_tmp); cudaFree(ctx->d_sort_hist);
     delete ctx;
 }
 
@@ -400,6 +403,25 @@ static int check_batch(rfb_ctx *ctx, const rfb_batch *b, bool host) {
     return RFB_OK;
 }
 
+// key bytes that can be non-zero for this batch (byte 0..3 state, 4..7 pos, 8..11 stream)
+static uint32_t sort_key_bytes(const rfb_nfa *nfa, const rfb_batch *b, bool host_batch) {
+    auto bytes_of = [](uint64_t maxv) { uint32_t m = 0; for (int i = 0; i < 4; i++) if (maxv >> (8 * i)) m |= 1u << i; return m ? m : 1u; };
+    uint64_t max_steps = b->n_steps;
+    if (b->steps && host_batch) { max_steps = 0; for (uint64_t s = 0; s < b->n_streams; s++) max_steps = std::max<uint64_t>(max_steps, b->steps[s]); }
+    else if (b->steps) max_steps = 0xFFFFFFFFull;   // per-stream lengths live on the device in the device-pointer variant
+    const uint64_t max_pos = std::min<uint64_t>(0xFFFFFFFFull, (uint64_t)b->pos_base + max_steps);
+    const uint64_t max_stream = std::min<uint64_t>(0xFFFFFFFFull, (uint64_t)b->stream_id_base + b->n_streams);
+    return bytes_of(nfa->host.n_states) | (bytes_of(max_pos) << 4) | (bytes_of(max_stream) << 8);
+}
+
+static int sort_on_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, bool host_batch, rfb_match *d_records, uint64_t n, cudaStream_t st) {
+    if (n < 2) return RFB_OK;
+    CU(ctx, ensure(ctx->d_sort_tmp, ctx->d_sort_tmp_cap, (size_t)n));
+    CU(ctx, ensure(ctx->d_sort_hist, ctx->d_sort_hist_cap, sort_hist_words(n)));
+    CU(ctx, launch_sort_records(d_records, ctx->d_sort_tmp, n, sort_key_bytes(nfa, b, host_batch), ctx->d_sort_hist, st));
+    return RFB_OK;
+}
+
 int rfb_scan_collect(rfb_ctx *ctx, rfb_result *res) {
     if (!ctx || !res) return fail(ctx, RFB_E_INVALID, "NULL argument");
     cudaSetDevice(ctx->device);
@@ -457,7 +479,7 @@ int rfb_scan_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
     if (nfa->ctx != ctx) return fail(ctx, RFB_E_INVALID, "nfa belongs to another context");
     int rc = check_batch(ctx, b, false);
     if (rc) return rc;
-    if (flags & RFB_SCAN_SORT_RECORDS) return fail(ctx, RFB_E_UNSUPPORTED, "RFB_SCAN_SORT_RECORDS is only available through rfb_scan");
+    if ((flags & RFB_SCAN_SORT_RECORDS) && (flags & RFB_SCAN_ASYNC)) return fail(ctx, RFB_E_UNSUPPORTED, "RFB_SCAN_SORT_RECORDS needs the record count: not available with RFB_SCAN_ASYNC");
     if ((b->state_in || b->state_out) && nfa->parts.size() > 1) return fail(ctx, RFB_E_UNSUPPORTED, "resumable scans are not available for an NFA that is scanned in several parts");
     cudaSetDevice(ctx->device);
     (void)cudaGetLastError();   // a stale error of an unrelated earlier call must not be blamed on this launch
@@ -481,7 +503,12 @@ int rfb_scan_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
     ctx->last_symbols = b->steps ? 0 : b->n_streams * (unsigned long long)b->n_steps;
     ctx->last_launches = launches;
     if (flags & RFB_SCAN_ASYNC) return RFB_OK;
-    return rfb_scan_collect(ctx, res);
+    rc = rfb_scan_collect(ctx, res);
+    if (rc == RFB_OK && (flags & RFB_SCAN_SORT_RECORDS) && res->n_records > 1) {
+        rc = sort_on_device(ctx, nfa, b, false, res->records, res->n_records, st);
+        if (rc == RFB_OK) CU(ctx, cudaStreamSynchronize(st));
+    }
+    return rc;
 }
 
 int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flags, rfb_result *res) {
@@ -572,6 +599,10 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     ctx->last_launches = launches;
     rc = rfb_scan_collect(ctx, &dr);
     if (rc) return rc;
+    if ((flags & RFB_SCAN_SORT_RECORDS) && dr.n_records > 1) {
+        rc = sort_on_device(ctx, nfa, b, true, ctx->d_records, dr.n_records, st);
+        if (rc) return rc;
+    }
     if (want_counts) CU(ctx, cudaMemcpyAsync(res->counts, ctx->d_counts, (size_t)nfa->host.n_states * 8, cudaMemcpyDeviceToHost, st));
     if (dr.n_records) CU(ctx, cudaMemcpyAsync(res->records, ctx->d_records, dr.n_records * sizeof(rfb_match), cudaMemcpyDeviceToHost, st));
     if (b->state_out && state_words) CU(ctx, cudaMemcpyAsync(b->state_out, ctx->d_state_out, state_words * 4, cudaMemcpyDeviceToHost, st));
@@ -579,13 +610,6 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     res->n_matches = dr.n_matches; res->n_records = dr.n_records; res->n_dropped = dr.n_dropped;
     res->n_symbols = dr.n_symbols; res->n_rescanned = dr.n_rescanned; res->gpu_ms = dr.gpu_ms;
     res->n_launches = dr.n_launches;
-    if ((flags & RFB_SCAN_SORT_RECORDS) && res->n_records > 1) {
-        std::sort(res->records, res->records + res->n_records, [](const rfb_match &x, const rfb_match &y) {
-            if (x.stream != y.stream) return x.stream < y.stream;
-            if (x.pos != y.pos) return x.pos < y.pos;
-            return x.state < y.state;
-        });
-    }
     return RFB_OK;
 }
 

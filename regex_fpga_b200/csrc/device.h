@@ -83,6 +83,10 @@ cudaError_t launch_scan_warp(const NfaDev &nfa, const BatchDev &batch, const Out
                              int n_sms, cudaStream_t stream);
 cudaError_t launch_tb_cycles(const NfaDev &nfa, const uint32_t *cost, const uint8_t *lo, const uint8_t *hi, uint32_t n_steps,
                              unsigned long long *total, cudaStream_t stream);
+// canonical (stream, pos, state) order of records[0..n) on the device (sort.cu)
+cudaError_t launch_sort_records(rfb_match *records, rfb_match *tmp, unsigned long long n, uint32_t key_bytes, uint32_t *hist,
+                                cudaStream_t stream);
+size_t sort_hist_words(unsigned long long n);
 cudaError_t configure_kernels();
 constexpr size_t MAX_DYN_SMEM = 227 * 1024;   // per-CTA opt-in limit on sm_100
 

@@ -374,6 +374,30 @@ def test_host_path_chunked_overlap_matches_device_path(gpu_ctx, snort):
     assert ragged.n_symbols == int(steps.sum())
 
 
+def test_device_side_record_sort(gpu_ctx, snort):
+    """RFB_SCAN_SORT_RECORDS on the device path: a stable LSD radix sort over the 12-byte records must give exactly
+    the canonical (stream, pos, state) order, also with a large stream_id_base / pos_base (all key bytes in use)."""
+    import torch
+    nfa = gpu_ctx.nfa_from_entries(snort.entries)
+    n = 60000
+    dev = WL.make_batch_torch("whi", snort.lo, snort.hi, n, "cuda:0", 1500, 1536)
+    cap = 1 << 19
+    for sbase, pbase in ((0, 0), (0xF0000000, 0x7F000000)):
+        recs = torch.zeros(cap * 3, dtype=torch.int32, device="cuda:0")
+        r = nfa.scan_device(dev.data_ptr(), dev.numel(), n, 1500, 1536, None, recs.data_ptr(), cap, flags=R.SCAN_SORT_RECORDS,
+                            cuda_stream=torch.cuda.current_stream().cuda_stream, stream_id_base=sbase, pos_base=pbase)
+        assert r.n_records == r.n_matches > 100000
+        got = recs.cpu().numpy().view(np.uint32).reshape(-1, 3)[: r.n_records]
+        order = np.lexsort((got[:, 2], got[:, 1], got[:, 0]))
+        assert np.array_equal(order, np.arange(r.n_records))           # already sorted, ties impossible (records are unique)
+        assert int(got[:, 0].min()) >= sbase and int(got[:, 1].min()) >= pbase
+    unsorted = torch.zeros(cap * 3, dtype=torch.int32, device="cuda:0")
+    r2 = nfa.scan_device(dev.data_ptr(), dev.numel(), n, 1500, 1536, None, unsorted.data_ptr(), cap,
+                         cuda_stream=torch.cuda.current_stream().cuda_stream, stream_id_base=0xF0000000, pos_base=0x7F000000)
+    u = unsorted.cpu().numpy().view(np.uint32).reshape(-1, 3)[: r2.n_records]
+    assert sorted(map(tuple, u.tolist())) == list(map(tuple, got.tolist()))
+
+
 def test_large_batch_properties(gpu_ctx, snort):
     """Full-size-shaped batch (256K streams here; bench runs 1M): size-independent properties --
     counts are additive over any partition of the streams, independent of stream order, and the lane
