@@ -34,6 +34,7 @@ if ROOT not in sys.path:
 STREAM_LEN = 1500
 STRIDE = 1536
 SEED = 0x5EED0001
+E2E_FLAGS = 1   # RFB_SCAN_SORT_RECORDS: the end-to-end call returns records in canonical (stream, pos, state) order
 METRIC = "gbit_per_s_scanned_snort16"   # BASELINE.json: Gbit/s scanned (snort_16 NFA)
 
 
@@ -191,12 +192,12 @@ def run_e2e(args, torch, dist, nfa, batch, n, first, cap, n_states, n_matches, b
     torch.cuda.synchronize()
     host_np = host.numpy()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    out = nfa.scan(host_np, n, n_steps=STREAM_LEN, stride=STRIDE, record_capacity=cap, flags=0,
+    out = nfa.scan(host_np, n, n_steps=STREAM_LEN, stride=STRIDE, record_capacity=cap, flags=E2E_FLAGS,
                    stream_id_base=first)   # warm-up (allocates the staging buffers)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = nfa.scan(host_np, n, n_steps=STREAM_LEN, stride=STRIDE, record_capacity=cap, flags=0,
+        out = nfa.scan(host_np, n, n_steps=STREAM_LEN, stride=STRIDE, record_capacity=cap, flags=E2E_FLAGS,
                        stream_id_base=first)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps

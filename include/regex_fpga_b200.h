@@ -96,7 +96,8 @@ typedef struct rfb_batch {
 
 /* flags for rfb_scan / rfb_scan_device */
 #define RFB_SCAN_DEFAULT      0u
-#define RFB_SCAN_SORT_RECORDS 1u   /* records in canonical (stream,pos,state) ascending order */
+#define RFB_SCAN_SORT_RECORDS 1u   /* records in canonical (stream,pos,state) ascending order (sorted on the GPU;
+                                      rfb_scan_device: not together with RFB_SCAN_ASYNC) */
 #define RFB_SCAN_FORCE_WARP   2u   /* use only the general warp-per-stream kernel */
 #define RFB_SCAN_NO_COUNTS    4u   /* skip per-state counters */
 #define RFB_SCAN_ASYNC        8u   /* rfb_scan_device: enqueue only; call rfb_scan_collect later */
