@@ -51,11 +51,11 @@ struct Part {
     uint32_t *d_entries = nullptr;
     uint32_t *d_eptr = nullptr; unsigned long long *d_erec = nullptr; uint32_t *d_emembs = nullptr;
     uint8_t *d_blob = nullptr;
-    uint32_t *d_orig = nullptr, *d_map = nullptr;
+    uint32_t *d_orig = nullptr, *d_map = nullptr, *d_subof = nullptr;
     uint32_t *d_idof = nullptr, *d_virt_ptr = nullptr, *d_virt_ids = nullptr;
     void release() {
         cudaFree(d_entries); cudaFree(d_eptr); cudaFree(d_erec); cudaFree(d_emembs); cudaFree(d_blob);
-        cudaFree(d_orig); cudaFree(d_map); cudaFree(d_idof); cudaFree(d_virt_ptr); cudaFree(d_virt_ids);
+        cudaFree(d_orig); cudaFree(d_map); cudaFree(d_subof); cudaFree(d_idof); cudaFree(d_virt_ptr); cudaFree(d_virt_ids);
     }
 };
 
@@ -186,7 +186,7 @@ void rfb_ctx_destroy(rfb_ctx *ctx) {
 
 // ---- transition memory ---------------------------------------------------------------------------
 // builds the device copy of one part: edge-grouped CSR always, execution image when it fits
-static int upload_part(rfb_ctx *ctx, Part &p, std::string &err) {
+static int upload_part(rfb_ctx *ctx, Part &p, uint32_t n_states_full, std::string &err) {
     cudaError_t e;
     int rc = ecsr_build(p.sub, p.ecsr, err);
     if (rc) return rc;
@@ -204,7 +204,13 @@ static int upload_part(rfb_ctx *ctx, Part &p, std::string &err) {
     p.dev.row_ptr = p.d_entries;
     p.dev.trans = p.d_entries + h.n_states + 1;
     p.dev.eptr = p.d_eptr; p.dev.erec = p.d_erec; p.dev.emembs = p.d_emembs;
-    if (!p.to_orig.empty()) { UP(p.d_map, p.to_orig, uint32_t); p.dev.state_map = p.d_map; }
+    std::vector<uint32_t> sub_of_ref;                                   // reference id -> sub id (parts of a cut NFA only)
+    if (!p.to_orig.empty()) {
+        UP(p.d_map, p.to_orig, uint32_t); p.dev.state_map = p.d_map;
+        sub_of_ref.assign(n_states_full, 0xFFFFFFFFu);
+        for (uint32_t i = 0; i < p.to_orig.size(); i++) sub_of_ref[p.to_orig[i]] = i;
+        UP(p.d_subof, sub_of_ref, uint32_t); p.dev.sub_of_ref = p.d_subof;
+    }
     if (p.img.ok) {
         const Image &im = p.img;
         std::vector<uint32_t> orig = im.orig_of_id;                     // internal id -> REFERENCE state id
@@ -212,9 +218,15 @@ static int upload_part(rfb_ctx *ctx, Part &p, std::string &err) {
         std::vector<uint32_t> vptr(1, 0), vids;
         for (const auto &v : im.virt_of_cls1) { vids.insert(vids.end(), v.begin(), v.end()); vptr.push_back((uint32_t)vids.size()); }
         if (vptr.size() < 2) vptr.push_back(0);
+        std::vector<uint32_t> idof = im.id_of_orig;                     // REFERENCE state id -> internal id
+        if (!p.to_orig.empty()) {
+            for (auto &v : vids) v = p.to_orig[v];
+            idof.assign(n_states_full, 0xFFFFFFFFu);
+            for (uint32_t i = 0; i < p.to_orig.size(); i++) idof[p.to_orig[i]] = im.id_of_orig[i];
+        }
         UP(p.d_blob, im.blob, uint8_t);
         UP(p.d_orig, orig, uint32_t);
-        UP(p.d_idof, im.id_of_orig, uint32_t);
+        UP(p.d_idof, idof, uint32_t);
         UP(p.d_virt_ptr, vptr, uint32_t);
         UP(p.d_virt_ids, vids, uint32_t);
         p.dev.blob = p.d_blob; p.dev.orig_of_id = p.d_orig;
@@ -268,7 +280,7 @@ int rfb_nfa_from_entries(rfb_ctx *ctx, const uint32_t *entries, size_t n_entries
         if (!fallback.empty()) nfa->parts.swap(fallback);
     }
     for (Part &p : nfa->parts) {
-        rc = upload_part(ctx, p, err);
+        rc = upload_part(ctx, p, nfa->host.n_states, err);
         if (rc) { rfb_nfa_destroy(nfa); return rc == RFB_E_CUDA ? rc : fail(ctx, rc, err); }
     }
     if (nfa->parts.size() == 1) nfa->full = nfa->parts[0].dev;
@@ -461,6 +473,7 @@ static int enqueue_kernels(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b,
                 bd.chunk_streams = 0;        // the batch is resident once the first pass has consumed it
             }
             bd.count_symbols = first ? 1u : 0u;
+            bd.state_append = first ? 0u : 1u;
             const bool lane = p.img.ok && !(flags & RFB_SCAN_FORCE_WARP);
             if (lane) {
                 CU(ctx, launch_scan_lane(p.dev, bd, od, ctx->n_sms, st)); (*launches)++;
@@ -480,7 +493,6 @@ int rfb_scan_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
     int rc = check_batch(ctx, b, false);
     if (rc) return rc;
     if ((flags & RFB_SCAN_SORT_RECORDS) && (flags & RFB_SCAN_ASYNC)) return fail(ctx, RFB_E_UNSUPPORTED, "RFB_SCAN_SORT_RECORDS needs the record count: not available with RFB_SCAN_ASYNC");
-    if ((b->state_in || b->state_out) && nfa->parts.size() > 1) return fail(ctx, RFB_E_UNSUPPORTED, "resumable scans are not available for an NFA that is scanned in several parts");
     cudaSetDevice(ctx->device);
     (void)cudaGetLastError();   // a stale error of an unrelated earlier call must not be blamed on this launch
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
@@ -518,7 +530,6 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     if (rc) return rc;
     cudaSetDevice(ctx->device);
     (void)cudaGetLastError();
-    if ((b->state_in || b->state_out) && nfa->parts.size() > 1) return fail(ctx, RFB_E_UNSUPPORTED, "resumable scans are not available for an NFA that is scanned in several parts");
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
     const size_t padded = ((size_t)b->data_bytes + 15) / 16 * 16 + 16;
     CU(ctx, ensure(ctx->d_data, ctx->d_data_cap, padded));

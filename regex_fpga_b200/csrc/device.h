@@ -35,6 +35,7 @@ struct BatchDev {
     unsigned int state_cap;
     const unsigned int *state_in;
     unsigned int *state_out;
+    unsigned int state_append;   // parts after the first add their members to the set the earlier parts wrote
 };
 
 struct OutDev {
@@ -54,6 +55,7 @@ struct NfaDev {
     const unsigned long long *erec;   // [n_edges]
     const uint32_t *emembs;      // [n_sets * 8]
     const uint32_t *state_map;   // general kernel: state id of this (sub-)NFA -> reference state id; NULL = identity
+    const uint32_t *sub_of_ref;  // reference state id -> state id of this sub-NFA (0xFFFFFFFF: other part); NULL = identity
     // execution image
     const uint8_t *blob;         // ImageHeader::blob_bytes bytes, 16-byte aligned
     const uint32_t *orig_of_id;  // [n_slots]

@@ -102,9 +102,9 @@ __device__ __noinline__ bool ring_contains(uint32_t lb, uint32_t from, uint32_t 
 // S_{n_steps} of a finished stream = sticky bits + the ring's new entries + the never-materialised targets of the
 // accelerated state for the last symbol (cls1 = pcls).
 __device__ __noinline__ void lane_export_state(const uint32_t *orig_of_id, const uint32_t *virt_ptr, const uint32_t *virt_ids,
-                                               unsigned int *dst, uint32_t cap, uint64_t P0, uint64_t P1, uint32_t lb,
+                                               unsigned int *dst, uint32_t cap, bool append, uint64_t P0, uint64_t P1, uint32_t lb,
                                                uint32_t from, uint32_t to, uint32_t row, uint32_t rmask, uint32_t pcls) {
-    uint32_t n = 0;
+    uint32_t n = append ? dst[0] : 0u;                 // an earlier part's overflow mark (0xFFFFFFFF) stays an overflow
     for (int w = 0; w < 2; w++) {
         uint64_t bits = w ? P1 : P0;
         while (bits) {
@@ -200,7 +200,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                 } else if (k == nsteps) {
                     if (batch.state_out)
                         lane_export_state(nfa.orig_of_id, nfa.virt_ptr, nfa.virt_ids, batch.state_out + (size_t)sid * (1u + batch.state_cap),
-                                          batch.state_cap, P0, P1, lb, rp, re, ROW, RMASK, pcls);
+                                          batch.state_cap, batch.state_append != 0, P0, P1, lb, rp, re, ROW, RMASK, pcls);
                     have = false;
                 }
             }
@@ -210,7 +210,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     if (sid >= batch.n_streams) break;
                     nsteps = batch.steps ? batch.steps[sid] : batch.n_steps;
                     if (nsteps) break;
-                    if (batch.state_out)
+                    if (batch.state_out && !batch.state_append)
                         carry_state(batch.state_in ? batch.state_in + (size_t)sid * (1u + batch.state_cap) : nullptr,
                                     batch.state_out + (size_t)sid * (1u + batch.state_cap), batch.state_cap);
                 }
@@ -227,6 +227,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     bool fits = true;
                     for (uint32_t q = 0; q < ns; q++) {
                         const uint32_t id = nfa.id_of_orig[stt[1 + q]];
+                        if (id == 0xFFFFFFFFu) continue;          // a state of another part
                         if (id < nsb) { if (W == 1 || id < 64) P0 |= 1ull << (id & 63); else P1 |= 1ull << (id & 63); }
                         else if (((wp + ROW) & RMASK) == rp) fits = false;
                         else { ring_st(lb + wp, id); wp = (wp + ROW) & RMASK; }
@@ -440,8 +441,16 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
         bool dense = false;
         if (batch.state_in) {   // resume from the set an earlier call left
             const unsigned int *stt = batch.state_in + (size_t)sid * (1u + batch.state_cap);
-            ncur = min(stt[0], batch.state_cap);
-            for (uint32_t i = lane; i < ncur; i += 32) list_cur[i] = stt[1 + i];
+            const uint32_t ns = min(stt[0], batch.state_cap);
+            ncur = 0;
+            for (uint32_t base = 0; base < ns; base += 32) {             // keep the members that belong to this (sub-)NFA
+                const uint32_t i = base + lane;
+                uint32_t s = i < ns ? stt[1 + i] : 0xFFFFFFFFu;
+                if (i < ns && nfa.sub_of_ref) s = nfa.sub_of_ref[s];
+                const uint32_t m = __ballot_sync(0xffffffffu, s != 0xFFFFFFFFu);
+                if (s != 0xFFFFFFFFu) list_cur[ncur + __popc(m & ((1u << lane) - 1u))] = s;
+                ncur += __popc(m);
+            }
         } else if (lane == 0) list_cur[0] = 0;                            // Design/FPGA.v:146-147
         __syncwarp();
         for (uint32_t k = 0; k < nsteps; k++) {
@@ -500,9 +509,11 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
         }
         if (batch.state_out) {   // S_{n_steps}: handed to the caller instead of being dropped
             unsigned int *dst = batch.state_out + (size_t)sid * (1u + batch.state_cap);
-            const bool fits = !dense && ncur <= batch.state_cap;
-            if (lane == 0) dst[0] = fits ? ncur : 0xFFFFFFFFu;
-            if (fits) for (uint32_t i = lane; i < ncur; i += 32) dst[1 + i] = list_cur[i];
+            const uint32_t n0 = batch.state_append ? dst[0] : 0u;          // an earlier part's overflow mark stays
+            const bool fits = !dense && n0 != 0xFFFFFFFFu && n0 + ncur <= batch.state_cap;
+            __syncwarp();
+            if (lane == 0) dst[0] = fits ? n0 + ncur : 0xFFFFFFFFu;
+            if (fits) for (uint32_t i = lane; i < ncur; i += 32) dst[1 + n0 + i] = smap ? smap[list_cur[i]] : list_cur[i];
         }
         // leave both bit vectors clean for the next stream (S_{n_steps} is never examined, TB:71-86)
         if (!dense) { for (uint32_t i = lane; i < ncur; i += 32) bits_cur[list_cur[i] >> 5] = 0; }

@@ -326,8 +326,13 @@ def test_config5_replicated_large_nfa_adversarial(gpu_ctx, snort):
     steps[::3] = 100
     rag = nfa.scan(data, data.shape[0], stride=1536, steps=steps)
     assert rag.n_symbols == int(steps.sum())
-    with pytest.raises(R.RfbError):                                  # resumable scans need a single-part NFA
-        nfa.scan(data, data.shape[0], n_steps=10, stride=1536, want_state=True)
+    # resumable scans across the parts: every part imports its own members and appends them on export
+    sub = np.ascontiguousarray(data[:24])
+    whole = nfa.scan(sub, 24, n_steps=1500, stride=1536)
+    a = nfa.scan(sub, 24, n_steps=700, stride=1536, want_state=True, state_cap=255)
+    assert not np.any(a.state[:, 0] == R.STATE_OVERFLOW) and a.state[:, 0].max() > 7
+    b = nfa.scan(np.ascontiguousarray(sub[:, 700:]), 24, n_steps=800, stride=1536 - 700, state_in=a.state, pos_base=700)
+    assert sorted(recs_tuple(a.records) + recs_tuple(b.records)) == recs_tuple(whole.records)
 
 
 def test_unsplittable_large_nfa_uses_general_kernel(gpu_ctx):
