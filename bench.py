@@ -192,13 +192,17 @@ def run_e2e(args, torch, dist, nfa, batch, n, first, cap, n_states, n_matches, b
     torch.cuda.synchronize()
     host_np = host.numpy()
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    out = nfa.scan(host_np, n, n_steps=STREAM_LEN, stride=STRIDE, record_capacity=cap, flags=E2E_FLAGS,
-                   stream_id_base=first)   # warm-up (allocates the staging buffers)
+    # results land in pinned host arrays the caller owns and reuses (a pageable destination costs ~5 ms per pass)
+    from regex_fpga_b200.engine import MATCH_DTYPE
+    recs_host = torch.empty(cap * 12, dtype=torch.uint8, pin_memory=True).numpy().view(MATCH_DTYPE)
+    counts_host = torch.empty(n_states, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+    out = nfa.scan(host_np, n, n_steps=STREAM_LEN, stride=STRIDE, records_out=recs_host, counts_out=counts_host,
+                   flags=E2E_FLAGS, stream_id_base=first)   # warm-up (allocates the staging buffers)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = nfa.scan(host_np, n, n_steps=STREAM_LEN, stride=STRIDE, record_capacity=cap, flags=E2E_FLAGS,
-                       stream_id_base=first)
+        out = nfa.scan(host_np, n, n_steps=STREAM_LEN, stride=STRIDE, records_out=recs_host, counts_out=counts_host,
+                       flags=E2E_FLAGS, stream_id_base=first)
     barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if dist is not None:

@@ -11,6 +11,7 @@ using namespace rfb;
 
 static thread_local std::string g_err = "";
 
+static constexpr unsigned MAX_CHUNKS = 256;
 struct rfb_ctx {
     int device = 0;
     int n_sms = 0;
@@ -20,7 +21,7 @@ struct rfb_ctx {
     cudaEvent_t ev_chunk[16] = {};          // chunk i resident
     ScanGlobals *g = nullptr;          // device
     ScanGlobals *g_host = nullptr;     // pinned
-    unsigned int *chunk_vals = nullptr; // pinned {1..16}: sources of the chunks_ready updates
+    unsigned int *chunk_vals = nullptr; // pinned {1..MAX_CHUNKS}: sources of the chunks_ready updates
     uint2 *rescan = nullptr;
     size_t rescan_cap = 0;
     // grow-only staging for rfb_scan (host-pointer variant)
@@ -155,13 +156,13 @@ int rfb_ctx_create(int device_id, rfb_ctx **out) {
         (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess ||
         (e = cudaMalloc(reinterpret_cast<void **>(&ctx->g), sizeof(ScanGlobals))) != cudaSuccess ||
         (e = cudaMallocHost(reinterpret_cast<void **>(&ctx->g_host), sizeof(ScanGlobals))) != cudaSuccess ||
-        (e = cudaMallocHost(reinterpret_cast<void **>(&ctx->chunk_vals), 16 * sizeof(unsigned int))) != cudaSuccess ||
+        (e = cudaMallocHost(reinterpret_cast<void **>(&ctx->chunk_vals), MAX_CHUNKS * sizeof(unsigned int))) != cudaSuccess ||
         (e = configure_kernels()) != cudaSuccess) {
         int rc = cuda_fail(nullptr, e, "context setup");
         rfb_ctx_destroy(ctx);
         return rc;
     }
-    for (unsigned i = 0; i < 16; i++) ctx->chunk_vals[i] = i + 1;
+    for (unsigned i = 0; i < MAX_CHUNKS; i++) ctx->chunk_vals[i] = i + 1;
     *out = ctx;
     return RFB_OK;
 }
@@ -579,7 +580,12 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     const bool lane_path = nfa->parts[0].img.ok && !(flags & RFB_SCAN_FORCE_WARP);
     uint64_t n_chunks = 1;
     if (lane_path && !b->offsets && b->n_streams >= 64 && b->stride > 0)
-        n_chunks = std::min<uint64_t>(16, std::max<uint64_t>(1, b->data_bytes / (64ull << 20)));
+    {
+        uint64_t max_chunks = 16, min_bytes = 64ull << 20;
+        if (const char *e = getenv("RFB_CHUNKS")) max_chunks = std::min<uint64_t>(MAX_CHUNKS, std::max(1, atoi(e)));
+        if (const char *e = getenv("RFB_CHUNK_MB")) min_bytes = (uint64_t)std::max(1, atoi(e)) << 20;
+        n_chunks = std::min<uint64_t>(max_chunks, std::max<uint64_t>(1, b->data_bytes / min_bytes));
+    }
     const uint64_t chunk_streams = n_chunks > 1 ? ((b->n_streams + n_chunks - 1) / n_chunks + 31) / 32 * 32 : 0;
     CU(ctx, cudaEventRecord(ctx->ev_chunk[0], st));                  // globals reset before the first flag write
     CU(ctx, cudaStreamWaitEvent(cs, ctx->ev_chunk[0], 0));

@@ -183,8 +183,10 @@ class Nfa:
     # -- host buffers in, host results out (H2D + kernels + D2H inside the call) --
     def scan(self, data, n_streams, n_steps=0, stride=0, offsets=None, steps=None, record_capacity=1 << 20,
              flags=SCAN_SORT_RECORDS, stream_id_base=0, want_counts=True, state_in=None, want_state=False,
-             state_cap=63, pos_base=0):
-        """state_in / want_state: resumable scans -- pass the `state` of the previous call's result to continue the
+             state_cap=63, pos_base=0, records_out=None, counts_out=None):
+        """records_out / counts_out: caller-owned result arrays (e.g. views of pinned memory, reused across calls)
+        instead of fresh numpy arrays; records_out fixes record_capacity to its length.
+        state_in / want_state: resumable scans -- pass the `state` of the previous call's result to continue the
         same streams (and pos_base = symbols already consumed) instead of starting from the reset state {0}."""
         data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
         b = rfb_batch()
@@ -218,8 +220,14 @@ class Nfa:
             b.state_out = state_out.ctypes.data
         if state_in is not None or want_state:
             b.state_cap = state_cap
-        counts = np.zeros(self.n_states, dtype=np.uint64) if want_counts else None
-        records = np.zeros(record_capacity, dtype=MATCH_DTYPE)
+        if counts_out is not None:
+            assert counts_out.dtype == np.uint64 and counts_out.size >= self.n_states and counts_out.flags.c_contiguous
+            want_counts = True
+        counts = counts_out if counts_out is not None else (np.zeros(self.n_states, dtype=np.uint64) if want_counts else None)
+        if records_out is not None:
+            assert records_out.dtype == MATCH_DTYPE and records_out.flags.c_contiguous
+            record_capacity = records_out.size
+        records = records_out if records_out is not None else np.empty(record_capacity, dtype=MATCH_DTYPE)
         r = rfb_result()
         r.counts = counts.ctypes.data if want_counts else None
         r.records = records.ctypes.data if record_capacity else None

@@ -367,6 +367,11 @@ def test_host_path_chunked_overlap_matches_device_path(gpu_ctx, snort):
     assert got.n_matches == r.n_matches and got.n_symbols == n * 1500
     assert np.array_equal(got.counts, counts.cpu().numpy().astype(np.uint64))
     assert recs_tuple(got.records) == want
+    # caller-owned (pinned) result arrays, as bench.py's e2e leg passes them
+    prec = torch.empty(cap * 12, dtype=torch.uint8, pin_memory=True).numpy().view(R.engine.MATCH_DTYPE)
+    pcnt = torch.empty(snort.n_states, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+    own = nfa.scan(host, n, n_steps=1500, stride=1536, records_out=prec, counts_out=pcnt, stream_id_base=7)
+    assert own.records.base is not None and recs_tuple(own.records) == want and np.array_equal(pcnt, got.counts)
     steps = np.full(n, 1500, np.uint32)
     steps[::5] = 700
     steps[3::7] = 0
