@@ -53,10 +53,11 @@ struct Part {
     uint32_t *d_eptr = nullptr; unsigned long long *d_erec = nullptr; uint32_t *d_emembs = nullptr;
     uint8_t *d_blob = nullptr;
     uint32_t *d_orig = nullptr, *d_map = nullptr, *d_subof = nullptr;
-    uint32_t *d_idof = nullptr, *d_virt_ptr = nullptr, *d_virt_ids = nullptr;
+    uint32_t *d_idof = nullptr, *d_dta = nullptr, *d_mem_ptr = nullptr;
+    uint16_t *d_dt = nullptr, *d_act = nullptr, *d_mem_ids = nullptr;
     void release() {
         cudaFree(d_entries); cudaFree(d_eptr); cudaFree(d_erec); cudaFree(d_emembs); cudaFree(d_blob);
-        cudaFree(d_orig); cudaFree(d_map); cudaFree(d_subof); cudaFree(d_idof); cudaFree(d_virt_ptr); cudaFree(d_virt_ids);
+        cudaFree(d_orig); cudaFree(d_map); cudaFree(d_subof); cudaFree(d_idof); cudaFree(d_dta); cudaFree(d_mem_ptr); cudaFree(d_dt); cudaFree(d_act); cudaFree(d_mem_ids);
     }
 };
 
@@ -115,6 +116,7 @@ static ImageOptions default_image_options() {
     if (const char *s = std::getenv("RFB_STICKY_WORDS")) opt.sticky_words = std::atoi(s);
     if (const char *s = std::getenv("RFB_BUCKET_BITS")) opt.bucket_bits = std::atoi(s);
     if (const char *s = std::getenv("RFB_STICKY_MIN_SELF")) opt.sticky_min_self = std::atoi(s);
+    if (const char *s = std::getenv("RFB_DFA_STATES")) { const int v = std::atoi(s); if (v <= 0) opt.accel = 0; else opt.dfa_max_states = (uint32_t)v; }
     // the per-stream rings (16 entries x 1024 streams x 2 bytes) share the SM's shared memory with the tables
     opt.max_bytes = (uint32_t)(MAX_DYN_SMEM - 16 * LANE_THREADS * 2 - 64);
     return opt;
@@ -216,22 +218,27 @@ static int upload_part(rfb_ctx *ctx, Part &p, uint32_t n_states_full, std::strin
         const Image &im = p.img;
         std::vector<uint32_t> orig = im.orig_of_id;                     // internal id -> REFERENCE state id
         if (!p.to_orig.empty()) for (auto &o : orig) if (o != 0xFFFFFFFFu) o = p.to_orig[o];
-        std::vector<uint32_t> vptr(1, 0), vids;
-        for (const auto &v : im.virt_of_cls1) { vids.insert(vids.end(), v.begin(), v.end()); vptr.push_back((uint32_t)vids.size()); }
-        if (vptr.size() < 2) vptr.push_back(0);
         std::vector<uint32_t> idof = im.id_of_orig;                     // REFERENCE state id -> internal id
         if (!p.to_orig.empty()) {
-            for (auto &v : vids) v = p.to_orig[v];
             idof.assign(n_states_full, 0xFFFFFFFFu);
             for (uint32_t i = 0; i < p.to_orig.size(); i++) idof[p.to_orig[i]] = im.id_of_orig[i];
         }
         UP(p.d_blob, im.blob, uint8_t);
         UP(p.d_orig, orig, uint32_t);
         UP(p.d_idof, idof, uint32_t);
-        UP(p.d_virt_ptr, vptr, uint32_t);
-        UP(p.d_virt_ids, vids, uint32_t);
+        std::vector<uint16_t> mem_ids = im.dfa.mem_ids;
+        if (mem_ids.empty()) mem_ids.push_back(0);
+        UP(p.d_dt, im.dfa.dt, uint16_t);
+        UP(p.d_dta, im.dfa.dta, uint32_t);
+        std::vector<uint16_t> act = im.dfa.act;
+        if (act.empty()) act.push_back(0);
+        UP(p.d_act, act, uint16_t);
+        UP(p.d_mem_ptr, im.dfa.mem_ptr, uint32_t);
+        UP(p.d_mem_ids, mem_ids, uint16_t);
         p.dev.blob = p.d_blob; p.dev.orig_of_id = p.d_orig;
-        p.dev.id_of_orig = p.d_idof; p.dev.virt_ptr = p.d_virt_ptr; p.dev.virt_ids = p.d_virt_ids;
+        p.dev.id_of_orig = p.d_idof;
+        p.dev.dfa_dt = p.d_dt; p.dev.dfa_dta = p.d_dta; p.dev.dfa_act = p.d_act;
+        p.dev.dfa_mem_ptr = p.d_mem_ptr; p.dev.dfa_mem_ids = p.d_mem_ids;
         p.dev.h = im.h;
     }
 #undef UP

@@ -60,8 +60,12 @@ struct NfaDev {
     const uint8_t *blob;         // ImageHeader::blob_bytes bytes, 16-byte aligned
     const uint32_t *orig_of_id;  // [n_slots]
     const uint32_t *id_of_orig;  // [n_states]
-    const uint32_t *virt_ptr;    // [n_cls1 + 1]: never-materialised targets of the accelerated state per cls1 ...
-    const uint32_t *virt_ids;    // ... as original state ids
+    // start DFA (image.cpp): tables in global memory
+    const uint16_t *dfa_dt;      // [dfa_states * dfa_ncls]: next state | 0x8000 if the transition has an insertion list
+    const uint32_t *dfa_dta;     // [dfa_states * dfa_ncls]: index of that list in dfa_act
+    const uint16_t *dfa_act;     // insertion lists: internal id | 0x8000 if another entry follows
+    const uint32_t *dfa_mem_ptr; // [dfa_states + 1]: never-materialised members of each DFA state ...
+    const uint16_t *dfa_mem_ids; // ... as internal ids
     ImageHeader h;
 };
 

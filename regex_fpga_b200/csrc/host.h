@@ -65,7 +65,8 @@ struct ImageOptions {
     int sticky_words = 0;       // 0 = auto (1 or 2)
     int sticky_min_self = 16;   // a state is mask-resident if it self-loops on >= this many symbols
     int bucket_bits = -1;       // -1 = auto; buckets per branching state = 1 << bucket_bits
-    int accel = 1;              // build the two-symbol start table for the busiest sticky state
+    int accel = 1;              // build the start DFA for the always-active sticky state
+    uint32_t dfa_max_states = 16384;   // <= 32766 (15-bit ids)
     uint32_t max_bytes = 200 * 1024;
 };
 
@@ -84,8 +85,9 @@ struct ImageHeader {  // mirrored on the device (passed by value to the kernels)
     uint32_t srow_base;     // first slot of the sticky rows (sized per state, see off_sdesc)
     // byte offsets of the sections inside the blob (all 16-byte aligned)
     uint32_t off_tab, off_mask, off_memb, off_sdesc;   // sdesc[b] = row base | (row mask << 16) of sticky bit b
-    // two-symbol start table of the accelerated sticky state (bit 0); accel == 0: absent
-    uint32_t accel, nc2, off_cmap, off_t2, off_tl2;
+    uint32_t off_cmap;      // cmap[c] = start-DFA symbol class | h(c) << 16
+    // start DFA of the always-active sticky state (bit 0), tables in global memory; accel == 0: absent
+    uint32_t accel, dfa_ncls, dfa_states;
     uint32_t blob_bytes;
 };
 
@@ -98,9 +100,18 @@ struct Image {
     std::vector<uint32_t> id_of_orig;  // original state id -> internal id
     uint32_t n_sticky = 0;
     uint32_t n_sticky_dropped = 0;                      // self-looping states that did not fit the mask (run as ordinary states)
-    // accelerated sticky state (host-side description for the verifier)
-    uint32_t accel_state = 0xFFFFFFFFu;                 // original id
-    std::vector<std::vector<uint32_t>> virt_of_cls1;   // class of c1 -> virtual targets (original ids)
+    // start DFA (see image.cpp): the successors of the always-active state A (bit 0) that are neither sticky nor
+    // accepting are never materialised; a per-stream DFA state d stands for the set of them that is active.
+    uint32_t accel_state = 0xFFFFFFFFu;   // original id of A
+    struct Dfa {
+        uint32_t ncls = 1, n = 1;          // symbol classes, DFA states (0 = A not active yet, 1 = A alone)
+        std::vector<uint16_t> dt;          // [n * ncls]: next state | 0x8000 if the transition has an insertion list
+        std::vector<uint32_t> dta;         // [n * ncls]: index of that list in act
+        std::vector<uint16_t> act;         // insertion lists: internal id | 0x8000 if another entry follows
+        std::vector<uint32_t> mem_ptr;     // [n + 1]: members of each DFA state ...
+        std::vector<uint16_t> mem_ids;     // ... as internal ids (never sticky, never accepting)
+        uint32_t n_frontier = 0;           // states whose rows fall back to a shorter history
+    } dfa;
 };
 
 // tab entry encoding

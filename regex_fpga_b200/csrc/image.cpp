@@ -21,12 +21,16 @@
 //       a <= b            : edge taken iff c == a or c == b
 //       a == 0xFF > b     : indirect, target_id = index of the chain
 //       a in {0xFE,0xFD}  : edge taken iff c is in class set (0xFE - a) * 253 + b   (b < 253)
-//   * the busiest sticky state A (in an unanchored ruleset: the global ".*" state, active for ever)
-//     gets bit 0 and a two-symbol start table: its targets X that are neither sticky nor accepting are
-//     never materialised; instead T2[cls1(c_k)][cls2(c_k+1)] lists the successors of those X on the
-//     next symbol (the NFA step is a union over active states, so composing two steps of one always-
-//     firing state is exact).  cmap[c] = cls1 | cls2 << 8, T2 entries are 0xFFFF (none), a target id,
-//     or 0x8000 | offset of a target list.
+//   * the always-active sticky state A (in an unanchored ruleset: the global ".*" state, which self-loops on all
+//     256 symbols) gets bit 0 and a START DFA.  The states reachable from A through ordinary (neither sticky nor
+//     accepting) states are never materialised while the DFA can follow them: a per-stream DFA state d stands for
+//     the set members(d) of such states that is active, and one lookup DT[d][cls(c)] replaces the expansion of all
+//     of them (the NFA step is a union over active states, so tracking part of the set as a subset-construction
+//     state is exact).  Sticky, accepting and -- for states beyond the size budget -- ordinary successors that the
+//     next DFA state does not contain are listed per transition (an "insertion list") and enter the per-stream
+//     structures like any other target.  States beyond the budget resolve to the state of their longest tracked
+//     suffix history (Aho-Corasick failure links over the subset states), so no transition is ever missing.
+//     cmap[c] = class of c for the DFA | h(c) << 16.  The DFA tables live in global memory (L1/L2 resident).
 //   * accepting (zero-out-degree) states own the contiguous id range [acc_base, acc_base + n_acc):
 //     the kernel reports them when it pops them, without a table lookup.
 //   * state ids are internal (sticky ids < 64 * sticky_words); orig_of_id restores the reference's
@@ -97,37 +101,27 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
         edges[p].swap(keep);
     }
 
-    // ---- accelerated sticky state ---------------------------------------------------------------------
+    // ---- always-active sticky state ---------------------------------------------------------------------
     auto is_accept = [&](uint32_t s) { return rp[s] == rp[s + 1]; };
-    std::vector<Edge> virt_edges;    // A's edges to targets that are never materialised
-    std::vector<uint32_t> virt;      // those targets (original ids, sorted)
+    std::vector<Edge> a_edges;       // A's non-self edges: followed by the start DFA, not by A's row
     bool accel = false;
     if (opt.accel && !cand.empty()) {
-        // Prefer a state that is active for ever in every stream (entered from state 0 on all 256 symbols
-        // and self-looping on all of them: the global ".*" of an unanchored ruleset); otherwise the state
-        // with the most never-materialisable targets.
+        // A must self-loop on all 256 symbols (once entered it never leaves the set).  Prefer the state entered
+        // from state 0 on every symbol (the global ".*" of an unanchored ruleset), then the most edges.
         SymSet all256;
         for (uint32_t c = 0; c < 256; c++) all256.set(c);
         size_t best = 0; int best_n = 0;
         for (size_t b = 0; b < cand.size(); b++) {
-            int n = 0;
-            for (const Edge &e : edges[cand[b]]) n += (sticky_bit[e.tgt] < 0 && !is_accept(e.tgt));
-            if (n == 0) continue;
-            bool always = selfset[cand[b]] == all256;
-            if (always) { always = false; for (const Edge &e : edges[0]) if (e.tgt == cand[b] && e.syms == all256) always = true; }
-            if (always) n += 1000;
+            if (!(selfset[cand[b]] == all256) || edges[cand[b]].empty()) continue;
+            int n = 1 + (int)edges[cand[b]].size();
+            for (const Edge &e : edges[0]) if (e.tgt == cand[b] && e.syms == all256) n += 1000000;
             if (n > best_n) { best_n = n; best = b; }
         }
-        if (best_n >= 4) {
+        if (best_n > 0) {
             std::swap(cand[0], cand[best]);
             for (size_t b = 0; b < cand.size(); b++) sticky_bit[cand[b]] = (int32_t)b;
-            const uint32_t A = cand[0];
-            std::vector<Edge> keep;
-            for (const Edge &e : edges[A]) {
-                if (sticky_bit[e.tgt] < 0 && !is_accept(e.tgt)) { virt_edges.push_back(e); virt.push_back(e.tgt); }
-                else keep.push_back(e);
-            }
-            if (!virt_edges.empty()) { edges[A].swap(keep); accel = true; img.accel_state = A; }
+            a_edges.swap(edges[cand[0]]);
+            accel = true; img.accel_state = cand[0];
         }
     }
 
@@ -287,47 +281,110 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
         }
     }
 
-    // ---- two-symbol start table -------------------------------------------------------------------------
-    std::vector<uint32_t> cmap(256, 0);                       // per symbol: cls1 | cls2 << 8 | h(c) << 16
-    std::vector<uint16_t> t2(1, 0xFFFF), tl2;
-    uint32_t nc1 = 1, nc2 = 1;
+    // ---- start DFA --------------------------------------------------------------------------------------
+    std::vector<uint32_t> cmap(256, 0);                       // per symbol: DFA class | h(c) << 16
+    Image::Dfa &D = img.dfa;
+    D = Image::Dfa();
+    D.dt.assign(1, 0); D.dta.assign(1, 0); D.mem_ptr.assign(2, 0);
     if (accel) {
-        std::map<std::vector<uint32_t>, uint32_t> c1id, c2id;
-        std::vector<uint32_t> rep2;                         // representative symbol of each cls2
-        c1id[{}] = 0; img.virt_of_cls1.push_back({});
-        std::vector<uint32_t> cls1(256), cls2(256);
-        auto succ = [&](uint32_t X, uint32_t c) { std::vector<uint32_t> v; for (const Edge &e : edges[X]) if (e.syms.has(c)) v.push_back(e.tgt); return v; };
-        for (uint32_t c = 0; c < 256; c++) {
-            std::vector<uint32_t> v;
-            for (const Edge &e : virt_edges) if (e.syms.has(c)) v.push_back(e.tgt);
-            std::sort(v.begin(), v.end());
-            auto it = c1id.find(v);
-            if (it == c1id.end()) { it = c1id.emplace(v, (uint32_t)c1id.size()).first; img.virt_of_cls1.push_back(v); }
-            cls1[c] = it->second;
-            std::vector<uint32_t> sig;                      // behaviour of c on every virtual target
-            for (uint32_t X : virt) { for (uint32_t t : succ(X, c)) sig.push_back(t); sig.push_back(0xFFFFFFFFu); }
-            auto jt = c2id.find(sig);
-            if (jt == c2id.end()) { jt = c2id.emplace(sig, (uint32_t)c2id.size()).first; rep2.push_back(c); }
-            cls2[c] = jt->second;
+        auto ordinary = [&](uint32_t s) { return sticky_bit[s] < 0 && !is_accept(s); };
+        // states the DFA can hold: reachable from A through ordinary states
+        std::vector<char> in_r(N, 0);
+        std::vector<uint32_t> stack;
+        for (const Edge &e : a_edges) if (ordinary(e.tgt) && !in_r[e.tgt]) { in_r[e.tgt] = 1; stack.push_back(e.tgt); }
+        while (!stack.empty()) {
+            const uint32_t s = stack.back(); stack.pop_back();
+            for (const Edge &e : edges[s]) if (ordinary(e.tgt) && !in_r[e.tgt]) { in_r[e.tgt] = 1; stack.push_back(e.tgt); }
         }
-        nc1 = (uint32_t)c1id.size(); nc2 = (uint32_t)c2id.size();
-        if (nc1 > 255 || nc2 > 255 || (size_t)nc1 * nc2 > 16384) { img.why_not = "two-symbol start table too large"; }
-        else {
-            t2.assign((size_t)nc1 * nc2, 0xFFFF);
-            for (uint32_t i = 0; i < nc1; i++)
-                for (uint32_t j = 0; j < nc2; j++) {
-                    std::vector<uint32_t> tg;
-                    for (uint32_t X : img.virt_of_cls1[i]) for (uint32_t t : succ(X, rep2[j])) tg.push_back(img.id_of_orig[t]);
-                    std::sort(tg.begin(), tg.end());
-                    tg.erase(std::unique(tg.begin(), tg.end()), tg.end());
-                    if (tg.empty()) continue;
-                    for (uint32_t t : tg) if (t > 0x7FFF) ids_ok = false;
-                    if (tg.size() == 1) { t2[i * nc2 + j] = (uint16_t)tg[0]; continue; }
-                    if (tl2.size() + tg.size() > 0x7FFE) { ids_ok = false; continue; }
-                    t2[i * nc2 + j] = (uint16_t)(0x8000u | tl2.size());
-                    for (size_t q = 0; q < tg.size(); q++) tl2.push_back((uint16_t)(tg[q] | (q + 1 < tg.size() ? 0x8000u : 0u)));
+        // symbol classes: two symbols are equivalent iff no edge of A or of those states tells them apart
+        std::vector<uint32_t> cls(256, 0);
+        uint32_t ncls = 1;
+        {
+            std::map<SymSet, int> distinct;
+            for (const Edge &e : a_edges) distinct.emplace(e.syms, 0);
+            for (uint32_t s = 0; s < N; s++) if (in_r[s]) for (const Edge &e : edges[s]) distinct.emplace(e.syms, 0);
+            for (const auto &kv : distinct) {
+                std::map<std::pair<uint32_t, bool>, uint32_t> split;
+                for (uint32_t c = 0; c < 256; c++) {
+                    auto it = split.emplace(std::make_pair(cls[c], kv.first.has(c)), (uint32_t)split.size()).first;
+                    cls[c] = it->second;
                 }
-            for (uint32_t c = 0; c < 256; c++) cmap[c] = cls1[c] | (cls2[c] << 8);
+                ncls = (uint32_t)split.size();
+            }
+        }
+        std::vector<uint32_t> rep(ncls, 0xFFFFFFFFu);
+        for (uint32_t c = 0; c < 256; c++) if (rep[cls[c]] == 0xFFFFFFFFu) rep[cls[c]] = c;
+        for (uint32_t c = 0; c < 256; c++) cmap[c] = cls[c];
+
+        const size_t ACT_CAP = 6u << 20;                      // insertion-list entries (12 MB)
+        uint32_t budget = std::min<uint32_t>(std::max<uint32_t>(opt.dfa_max_states, ncls + 2), 32766);
+        for (;; budget = std::max<uint32_t>(ncls + 2, budget / 2)) {
+            // breadth-first subset construction; states keyed by their ordinary members (original ids, sorted)
+            std::map<std::vector<uint32_t>, uint32_t> id_of;
+            std::vector<std::vector<uint32_t>> members(2);
+            std::vector<uint32_t> fail(2, 1);
+            std::map<std::vector<uint16_t>, uint32_t> act_of;
+            id_of[{}] = 1;
+            D.dt.assign((size_t)2 * ncls, 0); D.dta.assign((size_t)2 * ncls, 0);
+            D.act.assign(1, 0);                                // index 0: unused
+            D.n_frontier = 0;
+            bool act_overflow = false;
+            std::vector<uint32_t> T, ord;
+            std::vector<uint16_t> lst;
+            for (uint32_t d = 1; d < members.size() && !act_overflow; d++) {
+                if (D.dt.size() < (size_t)(d + 1) * ncls) { D.dt.resize((size_t)(d + 1) * ncls, 0); D.dta.resize((size_t)(d + 1) * ncls, 0); }
+                bool fell_back = false;
+                for (uint32_t q = 0; q < ncls; q++) {
+                    const uint32_t c = rep[q];
+                    T.clear();
+                    for (const Edge &e : a_edges) if (e.syms.has(c)) T.push_back(e.tgt);
+                    for (uint32_t m : members[d]) for (const Edge &e : edges[m]) if (e.syms.has(c)) T.push_back(e.tgt);
+                    std::sort(T.begin(), T.end());
+                    T.erase(std::unique(T.begin(), T.end()), T.end());
+                    ord.clear(); lst.clear();
+                    for (uint32_t t : T) { if (ordinary(t)) ord.push_back(t); else lst.push_back((uint16_t)img.id_of_orig[t]); }
+                    uint32_t nd;
+                    auto it = id_of.find(ord);
+                    if (it != id_of.end()) nd = it->second;
+                    else if (members.size() < budget) {
+                        nd = (uint32_t)members.size();
+                        id_of.emplace(ord, nd);
+                        members.push_back(ord);
+                        fail.push_back(d == 1 ? 1u : (uint32_t)(D.dt[(size_t)fail[d] * ncls + q] & 0x7FFFu));
+                    } else {
+                        // beyond the budget: continue from the longest tracked suffix history (its state holds a
+                        // subset of ord) and insert the rest explicitly
+                        fell_back = true;
+                        nd = d == 1 ? 1u : (uint32_t)(D.dt[(size_t)fail[d] * ncls + q] & 0x7FFFu);
+                        if (!std::includes(ord.begin(), ord.end(), members[nd].begin(), members[nd].end())) nd = 1;
+                        for (uint32_t t : ord) if (!std::binary_search(members[nd].begin(), members[nd].end(), t)) lst.push_back((uint16_t)img.id_of_orig[t]);
+                    }
+                    uint32_t at = 0;
+                    if (!lst.empty()) {
+                        std::sort(lst.begin(), lst.end());
+                        auto jt = act_of.find(lst);
+                        if (jt != act_of.end()) at = jt->second;
+                        else {
+                            at = (uint32_t)D.act.size();
+                            act_of.emplace(lst, at);
+                            for (size_t k = 0; k < lst.size(); k++) D.act.push_back((uint16_t)(lst[k] | (k + 1 < lst.size() ? 0x8000u : 0u)));
+                            if (D.act.size() > ACT_CAP) act_overflow = true;
+                        }
+                    }
+                    D.dt[(size_t)d * ncls + q] = (uint16_t)(nd | (at ? 0x8000u : 0u));
+                    D.dta[(size_t)d * ncls + q] = at;
+                }
+                D.n_frontier += fell_back;
+            }
+            if (act_overflow && budget > ncls + 2) continue;
+            if (act_overflow) { img.why_not = "start DFA insertion lists too large"; }
+            D.ncls = ncls; D.n = (uint32_t)members.size();
+            D.mem_ptr.assign(1, 0); D.mem_ids.clear();
+            for (const auto &m : members) {
+                for (uint32_t t : m) D.mem_ids.push_back((uint16_t)img.id_of_orig[t]);
+                D.mem_ptr.push_back((uint32_t)D.mem_ids.size());
+            }
+            break;
         }
     }
 
@@ -359,16 +416,15 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
     h.n_acc = n_acc;
     h.srow_base = srow_base;
     // Layout: the fixed-size tables first, at offsets that depend only on the sticky word count, so that the kernel
-    // addresses them with immediates: mask | cmap | sdesc | tab | t2 | tl2 | memb
+    // addresses them with immediates: mask | cmap | sdesc | tab | memb
     uint32_t off = 0;
     h.off_mask = off;  off += 256u * 32u * (uint32_t)W;
     h.off_cmap = off;  off += 1024;
     h.off_sdesc = off; off += nsb * 4;
     h.off_tab = off;   off = align16(off + (uint32_t)tab.size() * 4);
     h.accel = accel ? 1u : 0u;
-    h.nc2 = nc2;
-    h.off_t2 = off;    off = align16(off + (uint32_t)t2.size() * 2);
-    h.off_tl2 = off;   off = align16(off + (uint32_t)std::max<size_t>(8, tl2.size()) * 2);
+    h.dfa_ncls = D.ncls;
+    h.dfa_states = D.n;
     h.off_memb = off;  off = align16(off + (uint32_t)memb.size() * 4);
     h.blob_bytes = off;
     if (img.why_not.empty() && off > opt.max_bytes) img.why_not = "tables need " + std::to_string(off) + " bytes of shared memory (limit " + std::to_string(opt.max_bytes) + ")";
@@ -378,8 +434,6 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
     std::memcpy(&img.blob[h.off_memb], memb.data(), memb.size() * 4);
     std::memcpy(&img.blob[h.off_sdesc], sdesc.data(), sdesc.size() * 4);
     std::memcpy(&img.blob[h.off_cmap], cmap.data(), 1024);
-    std::memcpy(&img.blob[h.off_t2], t2.data(), t2.size() * 2);
-    if (!tl2.empty()) std::memcpy(&img.blob[h.off_tl2], tl2.data(), tl2.size() * 2);
 
     img.orig_of_id.assign(tab.size(), 0xFFFFFFFFu);
     for (uint32_t s = 0; s < N; s++) if (img.id_of_orig[s] < img.orig_of_id.size()) img.orig_of_id[img.id_of_orig[s]] = s;
@@ -427,9 +481,13 @@ void image_successors(const Image &img, uint32_t s, uint32_t c, std::vector<uint
         const uint64_t bit = 1ull << (id & 63);
         if (K[id >> 6] & bit) ids.push_back(id);
         if (M[id >> 6] & bit) { idx = (sdesc[id] & 0xFFFFu) + (hf & (sdesc[id] >> 16)); walk = true; }
-        if (h.accel && id == 0) {   // targets reached only through the two-symbol table (checked in image_verify)
+        if (h.accel && id == 0) {   // A's edges are followed by the start DFA: row of DFA state 1 (A alone)
             const uint32_t *cmap = reinterpret_cast<const uint32_t *>(&img.blob[h.off_cmap]);
-            for (uint32_t X : img.virt_of_cls1[cmap[c] & 0xFF]) ids.push_back(img.id_of_orig[X]);
+            const Image::Dfa &D = img.dfa;
+            const size_t at = (size_t)1 * D.ncls + (cmap[c] & 0xFF);
+            const uint32_t nd = D.dt[at] & 0x7FFFu;
+            for (uint32_t j = D.mem_ptr[nd]; j < D.mem_ptr[nd + 1]; j++) ids.push_back(D.mem_ids[j]);
+            if (D.dt[at] & 0x8000u) for (uint32_t q = D.dta[at];; q++) { ids.push_back(D.act[q] & 0x7FFFu); if (!(D.act[q] & 0x8000u)) break; }
         }
     } else if (id - h.acc_base < h.n_acc) {
         if (accepting) *accepting = true;
@@ -475,29 +533,56 @@ int image_verify(const Nfa &nfa, const Image &img, std::string &err) {
             }
         }
     }
-    if (img.h.accel) {   // T2[cls1(c1)][cls2(c2)] == successors on c2 of the virtual targets of A on c1
+    if (img.h.accel) {
+        // Start DFA: for every DFA state d >= 1 and every symbol c,
+        //   members(next) + insertion list  ==  successors on c of members(d) and of A (A's self loop aside),
+        // members are ordinary states, and state 0 (A not active yet) is inert.
         const ImageHeader &h = img.h;
+        const Image::Dfa &D = img.dfa;
         const uint32_t *cmap = reinterpret_cast<const uint32_t *>(&img.blob[h.off_cmap]);
-        const uint16_t *t2 = reinterpret_cast<const uint16_t *>(&img.blob[h.off_t2]);
-        const uint16_t *tl2 = reinterpret_cast<const uint16_t *>(&img.blob[h.off_tl2]);
-        for (uint32_t c1 = 0; c1 < 256; c1++) {
-            const std::vector<uint32_t> &V = img.virt_of_cls1[cmap[c1] & 0xFF];
-            for (uint32_t X : V)
-                if (img.id_of_orig[X] < h.nsb || rp[X] == rp[X + 1]) { err = "two-symbol table hides a sticky or accepting state"; return RFB_E_INTERNAL; }
-            for (uint32_t c2 = 0; c2 < 256; c2++) {
+        const uint32_t A = img.accel_state;
+        if (img.id_of_orig[A] != 0 || D.n < 2 || D.dt.size() != (size_t)D.n * D.ncls || D.mem_ptr.size() != D.n + 1) { err = "start DFA is malformed"; return RFB_E_INTERNAL; }
+        for (uint32_t q = 0; q < D.ncls; q++) if (D.dt[q] != 0) { err = "start DFA state 0 is not inert"; return RFB_E_INTERNAL; }
+        if (D.mem_ptr[1] != D.mem_ptr[2]) { err = "start DFA state 1 is not empty"; return RFB_E_INTERNAL; }
+        for (uint16_t m : D.mem_ids)
+            if (m < h.nsb || m - h.acc_base < h.n_acc) { err = "start DFA hides a sticky or accepting state"; return RFB_E_INTERNAL; }
+        // successor lists per (state, symbol) of the states the DFA can hold, from the CSR
+        std::vector<std::vector<uint32_t>> rows;              // rows[k * 256 + c]
+        std::vector<int32_t> row_of(N, -1);
+        auto row = [&](uint32_t s) -> size_t {
+            if (row_of[s] < 0) {
+                row_of[s] = (int32_t)(rows.size() / 256);
+                rows.resize(rows.size() + 256);
+                for (uint32_t j = rp[s]; j < rp[s + 1]; j++) {
+                    const uint32_t t = tr[j] & 0xFFFFFFu;
+                    if (!(s == A && t == A)) rows[(size_t)row_of[s] * 256 + (tr[j] >> 24)].push_back(t);
+                }
+            }
+            return (size_t)row_of[s] * 256;
+        };
+        for (uint32_t d = 1; d < D.n; d++) {
+            for (uint32_t c = 0; c < 256; c++) {
                 want.clear();
-                for (uint32_t X : V)
-                    for (uint32_t j = rp[X]; j < rp[X + 1]; j++) if ((tr[j] >> 24) == c2) want.push_back(tr[j] & 0xFFFFFFu);
+                { const size_t r = row(A) + c; want.insert(want.end(), rows[r].begin(), rows[r].end()); }
+                for (uint32_t j = D.mem_ptr[d]; j < D.mem_ptr[d + 1]; j++) {
+                    const size_t r = row(img.orig_of_id[D.mem_ids[j]]) + c;
+                    want.insert(want.end(), rows[r].begin(), rows[r].end());
+                }
                 std::sort(want.begin(), want.end());
                 want.erase(std::unique(want.begin(), want.end()), want.end());
                 got.clear();
-                const uint32_t x = t2[(cmap[c1] & 0xFF) * h.nc2 + ((cmap[c2] >> 8) & 0xFF)];
-                if (x != 0xFFFF) {
-                    if (x < 0x8000) got.push_back(img.orig_of_id[x]);
-                    else for (uint32_t q = x & 0x7FFF;; q++) { got.push_back(img.orig_of_id[tl2[q] & 0x7FFF]); if (!(tl2[q] & 0x8000)) break; }
-                }
+                const size_t at = (size_t)d * D.ncls + (cmap[c] & 0xFF);
+                const uint32_t nd = D.dt[at] & 0x7FFFu;
+                if (nd == 0 || nd >= D.n) { err = "start DFA transition leaves the table"; return RFB_E_INTERNAL; }
+                for (uint32_t j = D.mem_ptr[nd]; j < D.mem_ptr[nd + 1]; j++) got.push_back(img.orig_of_id[D.mem_ids[j]]);
+                if (D.dt[at] & 0x8000u)
+                    for (uint32_t q = D.dta[at];; q++) {
+                        if (q == 0 || q >= D.act.size()) { err = "start DFA insertion list out of range"; return RFB_E_INTERNAL; }
+                        got.push_back(img.orig_of_id[D.act[q] & 0x7FFFu]);
+                        if (!(D.act[q] & 0x8000u)) break;
+                    }
                 std::sort(got.begin(), got.end());
-                if (got != want) { err = "two-symbol start table disagrees with the CSR at symbols " + std::to_string(c1) + "," + std::to_string(c2); return RFB_E_INTERNAL; }
+                if (got != want) { err = "start DFA disagrees with the CSR at DFA state " + std::to_string(d) + " symbol " + std::to_string(c); return RFB_E_INTERNAL; }
             }
         }
     }

@@ -99,11 +99,11 @@ __device__ __noinline__ bool ring_contains(uint32_t lb, uint32_t from, uint32_t 
 }
 
 // ---- resumable scans: per-stream active sets as original state ids (rare paths, kept out of line) ----
-// S_{n_steps} of a finished stream = sticky bits + the ring's new entries + the never-materialised targets of the
-// accelerated state for the last symbol (cls1 = pcls).
-__device__ __noinline__ void lane_export_state(const uint32_t *orig_of_id, const uint32_t *virt_ptr, const uint32_t *virt_ids,
+// S_{n_steps} of a finished stream = sticky bits + the ring's new entries + the never-materialised members of the
+// stream's start-DFA state d (those that are not in the ring as well).
+__device__ __noinline__ void lane_export_state(const uint32_t *orig_of_id, const uint32_t *mem_ptr, const uint16_t *mem_ids,
                                                unsigned int *dst, uint32_t cap, bool append, uint64_t P0, uint64_t P1, uint32_t lb,
-                                               uint32_t from, uint32_t to, uint32_t row, uint32_t rmask, uint32_t pcls) {
+                                               uint32_t from, uint32_t to, uint32_t row, uint32_t rmask, uint32_t d) {
     uint32_t n = append ? dst[0] : 0u;                 // an earlier part's overflow mark (0xFFFFFFFF) stays an overflow
     for (int w = 0; w < 2; w++) {
         uint64_t bits = w ? P1 : P0;
@@ -118,8 +118,10 @@ __device__ __noinline__ void lane_export_state(const uint32_t *orig_of_id, const
         if (n < cap) dst[1 + n] = orig_of_id[ring_ld(lb + o)];
         n++;
     }
-    if (pcls) for (uint32_t j = virt_ptr[pcls]; j < virt_ptr[pcls + 1]; j++) {
-        if (n < cap) dst[1 + n] = virt_ids[j];
+    if (d) for (uint32_t j = mem_ptr[d]; j < mem_ptr[d + 1]; j++) {
+        const uint32_t id = mem_ids[j];
+        if (ring_contains(lb, from, to, row, rmask, id)) continue;
+        if (n < cap) dst[1 + n] = orig_of_id[id];
         n++;
     }
     dst[0] = n <= cap ? n : 0xFFFFFFFFu;
@@ -140,7 +142,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     constexpr uint32_t ROW = LANE_THREADS * 2;          // bytes between consecutive ring entries of one lane
     constexpr uint32_t RING = RING_CAP * ROW;
     constexpr uint32_t RMASK = RING - 1;
-    constexpr uint32_t NONE = 0xFFFFu;
+    constexpr uint32_t NONE = 0xFFFFFFFFu;
     constexpr int DRAIN_REPS = 1;                       // work items a lane may drain per iteration (2 measured slower)
     constexpr int OPEN_REPS = 1;                        // symbol steps a lane with nothing to drain may open per iteration (2 measured slower)
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + h.blob_bytes + RING);
@@ -151,11 +153,12 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     // fixed-size tables sit at offsets that depend only on W (image.cpp): immediates in the load instructions
     constexpr uint32_t OFF_CMAP = 256u * 32u * W, OFF_SDESC = OFF_CMAP + 1024u, OFF_TAB = OFF_SDESC + 64u * W * 4u;
     const uint32_t mask_s = sbase, cmap_s = sbase + OFF_CMAP, sdesc_s = sbase + OFF_SDESC, tab_s = sbase + OFF_TAB;
-    const uint32_t t2_s = sbase + h.off_t2, tl2_s = sbase + h.off_tl2, memb_s = sbase + h.off_memb;
+    const uint32_t memb_s = sbase + h.off_memb;
     const uint32_t lb = sbase + h.blob_bytes + threadIdx.x * 2;   // ring entry at byte offset o: lb + o; bank-conflict free
     const uint32_t gbase = h.gbase, nsb = h.nsb;
     const uint32_t nbm = (1u << h.bucket_bits) - 1u;
-    const uint32_t acc_base = h.acc_base, n_acc = h.n_acc, nc2 = h.nc2;
+    const uint32_t acc_base = h.acc_base, n_acc = h.n_acc, ncls = h.dfa_ncls;
+    const uint16_t *__restrict__ dfa_dt = nfa.dfa_dt;
     const bool accel = h.accel != 0;
     constexpr uint32_t MSTRIDE = 32u * W;
 
@@ -168,14 +171,14 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     uint64_t P0 = 0, P1 = 0, Pn0 = 0, Pn1 = 0;          // sticky sets (P1/Pn1 unused when W == 1)
     uint32_t rp = 0, re = 0, wp = 0;                    // ring byte offsets: next read, end of current set, next write
     uint32_t flo = 0, fhi = 0;                          // 64-bit membership filter of this step's new entries
-    uint32_t pcls = 0;                                  // cls1 of the previous symbol if state A fired on it
+    uint32_t d = 0;                                     // start-DFA state: 0 = A not active yet, 1 = A alone
     uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;            // remaining bytes of the current 16-byte chunk, next byte in b0[7:0]
     uint4 pre = make_uint4(0, 0, 0, 0);                 // the chunk after it
     uint32_t bufn = 0;
     const uint8_t *nextp = nullptr, *endp = nullptr;
     uint32_t sid = 0, k = 0, nsteps = 0;
     uint32_t c = 0, hf = 0, hc = 0;                     // symbol of the open step and its hashes
-    uint32_t x = NONE;                                  // pending two-symbol-table value
+    uint32_t x = NONE;                                  // next entry of a pending start-DFA insertion list
     uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;            // firing sticky bits not yet expanded
     uint32_t idx = 0;
     bool have = false, pend = false, walking = false, ovf = false;
@@ -199,8 +202,8 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     have = false; ovf = false;
                 } else if (k == nsteps) {
                     if (batch.state_out)
-                        lane_export_state(nfa.orig_of_id, nfa.virt_ptr, nfa.virt_ids, batch.state_out + (size_t)sid * (1u + batch.state_cap),
-                                          batch.state_cap, batch.state_append != 0, P0, P1, lb, rp, re, ROW, RMASK, pcls);
+                        lane_export_state(nfa.orig_of_id, nfa.dfa_mem_ptr, nfa.dfa_mem_ids, batch.state_out + (size_t)sid * (1u + batch.state_cap),
+                                          batch.state_cap, batch.state_append != 0, P0, P1, lb, rp, re, ROW, RMASK, d);
                     have = false;
                 }
             }
@@ -220,7 +223,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     const unsigned int need = sid / batch.chunk_streams + 1u;
                     while (*reinterpret_cast<const volatile unsigned int *>(batch.ready) < need) __nanosleep(256);
                 }
-                P0 = 0; P1 = 0; Pn0 = 0; Pn1 = 0; rp = 0; re = 0; wp = 0; flo = 0; fhi = 0; pcls = 0; k = 0;
+                P0 = 0; P1 = 0; Pn0 = 0; Pn1 = 0; rp = 0; re = 0; wp = 0; flo = 0; fhi = 0; d = 0; k = 0;
                 if (batch.state_in) {   // resume: the stream's active set as left by an earlier call
                     const unsigned int *stt = batch.state_in + (size_t)sid * (1u + batch.state_cap);
                     const uint32_t ns = min(stt[0], batch.state_cap);
@@ -266,13 +269,16 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             c = b0 & 0xFFu;
             b0 = __funnelshift_r(b0, b1, 8); b1 = __funnelshift_r(b1, b2, 8); b2 = __funnelshift_r(b2, b3, 8); b3 >>= 8;
             bufn--;
-            const uint32_t cm = lds32(cmap_s + c * 4);  // per-symbol descriptor: cls1 | cls2 << 8 | hash << 16
+            const uint32_t cm = lds32(cmap_s + c * 4);  // per-symbol descriptor: start-DFA class | hash << 16
             hf = cm >> 16;                              // symbol hash; a row uses its low bits
             hc = hf & nbm;
-            // two-symbol start table: successors of the never-materialised targets of state A
+            // start DFA: one lookup steps all the never-materialised successors of the always-active state A
             if (accel) {
-                x = lds16(t2_s + (pcls * nc2 + ((cm >> 8) & 0xFFu)) * 2);
-                pcls = (P0 & 1ull) ? (cm & 0xFFu) : 0u;
+                d = max(d, (uint32_t)P0 & 1u);          // A entered the set (it never leaves): 0 -> 1
+                const uint32_t at = d * ncls + (cm & 0xFFu);
+                const uint32_t e = __ldg(dfa_dt + at);
+                d = e & 0x7FFFu;
+                if (e & 0x8000u) x = __ldg(nfa.dfa_dta + at);   // sticky / accepting / untracked successors to insert
             }
             // sticky states: survivors P & K[c]; those in P & M[c] fire their rows
             {
@@ -307,10 +313,11 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             bool hit = false, look = walking;
             uint32_t t = 0;
             if (!walking) {
-                if (x != NONE) {                                  // two-symbol table hit: the target itself
+                if (x != NONE) {                                  // entry of a start-DFA insertion list: the target itself
                     hit = true;
-                    if (x < 0x8000u) { t = x; x = NONE; }
-                    else { const uint32_t tl = lds16(tl2_s + (x & 0x7FFFu) * 2); t = tl & 0x7FFFu; x = (tl & 0x8000u) ? x + 1 : NONE; }
+                    const uint32_t tl = __ldg(nfa.dfa_act + x);
+                    t = tl & 0x7FFFu;
+                    x = (tl & 0x8000u) ? x + 1 : NONE;
                 } else if (rp != re) {                            // a member of S_k
                     const uint32_t u = ring_ld(lb + rp);
                     rp = (rp + ROW) & RMASK;

@@ -3,7 +3,7 @@
 // symbol (list entries, table lookups, indirections, class tests, pushes, sticky "attention" events),
 // including the per-32-stream maximum that bounds a lock-step warp.  Used to size kernel design choices.
 //   g++ -O2 -std=c++17 -I regex_fpga_b200/csrc tools/image_stats.cpp regex_fpga_b200/csrc/{image,nfa,formats}.cpp -o /tmp/image_stats
-//   /tmp/image_stats <coe> <lo.mem> <hi.mem> [n_streams] [bucket_bits] [sticky_words]
+//   /tmp/image_stats <coe> <lo.mem> <hi.mem> [n_streams] [bucket_bits] [sticky_words] [dfa_max_states]
 #include "host.h"
 #include <algorithm>
 #include <cstdio>
@@ -26,7 +26,7 @@ int main(int argc, char **argv) {
     std::vector<uint32_t> E; std::vector<uint8_t> lo, hi; std::string err;
     if (coe_parse_file(argv[1], E, err) || mem_parse_file(argv[2], lo, err) || mem_parse_file(argv[3], hi, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
     int n_streams = argc > 4 ? atoi(argv[4]) : 1024;
-    ImageOptions opt; if (argc > 5) opt.bucket_bits = atoi(argv[5]); if (argc > 6) opt.sticky_words = atoi(argv[6]);
+    ImageOptions opt; if (argc > 5) opt.bucket_bits = atoi(argv[5]); if (argc > 6) opt.sticky_words = atoi(argv[6]); if (argc > 7) opt.dfa_max_states = atoi(argv[7]);
     Nfa nfa; Image img;
     if (nfa_from_entries(E.data(), E.size(), -1, nfa, err) || image_build(nfa, opt, img, err) || !img.ok) { fprintf(stderr, "image: %s %s\n", err.c_str(), img.why_not.c_str()); return 1; }
     const ImageHeader &h = img.h;
@@ -34,6 +34,7 @@ int main(int argc, char **argv) {
     const uint32_t *memb = (const uint32_t *)&img.blob[h.off_memb];
     const uint32_t *sdesc = (const uint32_t *)&img.blob[h.off_sdesc];
     const uint32_t W = h.sticky_words, ms = 32 * W, L = 1500;
+    printf("start DFA: %u states (%u beyond the budget), %u classes, %zu insertion-list entries\n", img.dfa.n, img.dfa.n_frontier, img.dfa.ncls, img.dfa.act.size());
     printf("image: slots %u gbase %u nsb %u W %u bucket_bits %u bytes %u sets %u sticky %u hash mul %u sh %u\n", h.n_slots, h.gbase, h.nsb, W, h.bucket_bits, h.blob_bytes, h.n_sets, img.n_sticky, h.hash_mul, h.hash_shift);
     Stats st[2];
     std::vector<std::vector<uint32_t>> per_sym_lookups(n_streams, std::vector<uint32_t>(L));
@@ -43,8 +44,8 @@ int main(int argc, char **argv) {
         uint64_t off = splitmix64(0x5EED0001ull ^ (uint64_t)j) % (std::min(lo.size(), hi.size()) - L + 1);
         Stats &s = st[j & 1];
         uint64_t P[2] = {0, 0};
-        uint32_t pcls = 0;
-        const uint32_t *cmap = (const uint32_t *)&img.blob[h.off_cmap]; const uint16_t *t2 = (const uint16_t *)&img.blob[h.off_t2], *tl2 = (const uint16_t *)&img.blob[h.off_tl2];
+        uint32_t d = 0;
+        const uint32_t *cmap = (const uint32_t *)&img.blob[h.off_cmap]; const Image::Dfa &D = img.dfa;
         std::vector<uint32_t> cur, nxt;
         if (h.start_id < h.nsb) P[h.start_id >> 6] |= 1ull << (h.start_id & 63); else cur.push_back(h.start_id);
         for (uint32_t k = 0; k < L; k++) {
@@ -65,9 +66,10 @@ int main(int argc, char **argv) {
                 }
             };
             if (h.accel) {
-                uint32_t cm = cmap[c], x = t2[pcls * h.nc2 + ((cm >> 8) & 0xFF)];
-                pcls = (P[0] & 1) ? (cm & 0xFF) : 0;
-                if (x != 0xFFFF) { s.t2hits++; if (x < 0x8000) push(x); else for (uint32_t q = x & 0x7FFF;; q++) { push(tl2[q] & 0x7FFF); if (!(tl2[q] & 0x8000)) break; } }
+                d = std::max<uint32_t>(d, P[0] & 1);
+                const size_t at = (size_t)d * D.ncls + (cmap[c] & 0xFF);
+                d = D.dt[at] & 0x7FFF;
+                if (D.dt[at] & 0x8000) { s.t2hits++; for (uint32_t q = D.dta[at];; q++) { push(D.act[q] & 0x7FFF); lk++; if (!(D.act[q] & 0x8000)) break; } }
             }
             s.entries += cur.size(); per_sym_entries[j][k] = cur.size();
             s.maxlist = std::max<double>(s.maxlist, cur.size());
