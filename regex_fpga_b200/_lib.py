@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librfb200.so")
+LIB_PATH = os.environ.get("RFB_LIB") or os.path.join(_HERE, "lib", "librfb200.so")   # RFB_LIB: kernel variants (tools/dev)
 
 
 class rfb_match(C.Structure):

@@ -19,6 +19,13 @@
 #include <cstdint>
 #include <cstdlib>
 
+#ifndef RFB_OPEN_REPS
+#define RFB_OPEN_REPS 1      // measured: see profiles/README.md
+#endif
+#ifndef RFB_DRAIN_REPS
+#define RFB_DRAIN_REPS 1
+#endif
+
 namespace rfb {
 
 // ------------------------------------------------------------------------------------------------
@@ -143,18 +150,21 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     constexpr uint32_t RING = RING_CAP * ROW;
     constexpr uint32_t RMASK = RING - 1;
     constexpr uint32_t NONE = 0xFFFFFFFFu;
-    constexpr int DRAIN_REPS = 1;                       // work items a lane may drain per iteration (2 measured slower)
-    constexpr int OPEN_REPS = 1;                        // symbol steps a lane with nothing to drain may open per iteration (2 measured slower)
+    // an iteration of the flat loop: up to open_reps symbol steps for a lane with nothing to drain, then up to
+    // drain_reps work items for a lane that has some
+    constexpr int open_reps = RFB_OPEN_REPS, drain_reps = RFB_DRAIN_REPS;
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + h.blob_bytes + RING);
     stage_image(smem, nfa.blob, h.blob_bytes, bar);
 
     // 32-bit shared-window addresses of the staged tables and of this lane's ring
-    const uint32_t sbase = smem_u32(smem);
+    // ptxas re-derives the shared window base (S2R CgaCtaId + LEA) and threadIdx at every use to save a register;
+    // routing both through a shuffle makes them opaque, so they stay in registers
+    const uint32_t sbase = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
     // fixed-size tables sit at offsets that depend only on W (image.cpp): immediates in the load instructions
     constexpr uint32_t OFF_CMAP = 256u * 32u * W, OFF_SDESC = OFF_CMAP + 1024u, OFF_TAB = OFF_SDESC + 64u * W * 4u;
     const uint32_t mask_s = sbase, cmap_s = sbase + OFF_CMAP, sdesc_s = sbase + OFF_SDESC, tab_s = sbase + OFF_TAB;
     const uint32_t memb_s = sbase + h.off_memb;
-    const uint32_t lb = sbase + h.blob_bytes + threadIdx.x * 2;   // ring entry at byte offset o: lb + o; bank-conflict free
+    const uint32_t lb = __shfl_sync(0xffffffffu, sbase + h.blob_bytes + threadIdx.x * 2, threadIdx.x & 31);   // ring entry at byte offset o: lb + o; bank-conflict free
     const uint32_t gbase = h.gbase, nsb = h.nsb;
     const uint32_t nbm = (1u << h.bucket_bits) - 1u;
     const uint32_t acc_base = h.acc_base, n_acc = h.n_acc, ncls = h.dfa_ncls;
@@ -187,7 +197,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     bool done = false;
     for (;;) {
 #pragma unroll 1
-        for (int rep = 0; rep < OPEN_REPS && !pend; rep++) {
+        for (int rep = 0; rep < open_reps && !pend; rep++) {
             if (have) {   // ---- close step k: current <= next (Design/FPGA.v:733-737) ----
                 P0 |= Pn0; Pn0 = 0;
                 if (W == 2) { P1 |= Pn1; Pn1 = 0; }
@@ -309,7 +319,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
         }
         if (done) break;
 #pragma unroll 1
-        for (int rep = 0; rep < DRAIN_REPS && pend; rep++) {   // ---- drain work items of the open step ----
+        for (int rep = 0; rep < drain_reps && pend; rep++) {   // ---- drain work items of the open step ----
             bool hit = false, look = walking;
             uint32_t t = 0;
             if (!walking) {
@@ -377,6 +387,7 @@ cudaError_t launch_scan_lane(const NfaDev &nfa, const BatchDev &batch, const Out
     unsigned long long want = (batch.n_streams + LANE_THREADS - 1) / LANE_THREADS;
     int grid = (int)(want < (unsigned long long)n_sms ? (want ? want : 1) : (unsigned long long)n_sms);
     const int cap = lane_ring_cap(nfa.h);
+
     const bool w1 = nfa.h.sticky_words == 1;
 #define RFB_LAUNCH(W_, C_) scan_lane_kernel<W_, C_><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out)
     if (cap == 64) { if (w1) RFB_LAUNCH(1, 64); else RFB_LAUNCH(2, 64); }

@@ -37,6 +37,7 @@ int main(int argc, char **argv) {
     printf("start DFA: %u states (%u beyond the budget), %u classes, %zu insertion-list entries\n", img.dfa.n, img.dfa.n_frontier, img.dfa.ncls, img.dfa.act.size());
     printf("image: slots %u gbase %u nsb %u W %u bucket_bits %u bytes %u sets %u sticky %u hash mul %u sh %u\n", h.n_slots, h.gbase, h.nsb, W, h.bucket_bits, h.blob_bytes, h.n_sets, img.n_sticky, h.hash_mul, h.hash_shift);
     Stats st[2];
+    std::vector<uint64_t> dhist;
     std::vector<std::vector<uint32_t>> per_sym_lookups(n_streams, std::vector<uint32_t>(L));
     std::vector<std::vector<uint32_t>> per_sym_entries(n_streams, std::vector<uint32_t>(L));
     for (int j = 0; j < n_streams; j++) {
@@ -69,6 +70,8 @@ int main(int argc, char **argv) {
                 d = std::max<uint32_t>(d, P[0] & 1);
                 const size_t at = (size_t)d * D.ncls + (cmap[c] & 0xFF);
                 d = D.dt[at] & 0x7FFF;
+                if (dhist.size() < D.n) dhist.resize(D.n, 0);
+                dhist[d]++;
                 if (D.dt[at] & 0x8000) { s.t2hits++; for (uint32_t q = D.dta[at];; q++) { push(D.act[q] & 0x7FFF); lk++; if (!(D.act[q] & 0x8000)) break; } }
             }
             s.entries += cur.size(); per_sym_entries[j][k] = cur.size();
@@ -96,6 +99,7 @@ int main(int argc, char **argv) {
         printf("%s: per symbol: t2hits %.3f entries %.3f lookups %.3f indirect %.3f class %.3f pushes %.3f attn %.3f inj %.3f sticky %.2f maxlist %.0f\n", t ? "hi" : "lo", s.t2hits / s.symbols,
                s.entries / s.symbols, s.lookups / s.symbols, s.indirect / s.symbols, s.cls / s.symbols, s.pushes / s.symbols, s.attn / s.symbols, s.inj / s.symbols, s.sticky / s.symbols, s.maxlist);
     }
+    { uint64_t tot = 0, cum = 0; for (auto v : dhist) tot += v; size_t i = 0; for (size_t H : {16, 64, 128, 256, 325, 512, 1024, 2048, 4096}) { for (; i < H && i < dhist.size(); i++) cum += dhist[i]; printf("DFA lookups landing in states < %zu (breadth-first order): %.4f\n", H, tot ? (double)cum / tot : 0.0); } }
     // lock-step warp bound: mean over (warp, symbol) of max over its 32 lanes
     double sum_max = 0, sum_tot = 0, sum_maxe = 0; uint64_t cnt = 0;
     for (int w0 = 0; w0 + 32 <= n_streams; w0 += 32)
