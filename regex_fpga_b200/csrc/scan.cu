@@ -180,7 +180,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     // busy and quiet streams balance automatically.
     uint64_t P0 = 0, P1 = 0, Pn0 = 0, Pn1 = 0;          // sticky sets (P1/Pn1 unused when W == 1)
     uint32_t rp = 0, re = 0, wp = 0;                    // ring byte offsets: next read, end of current set, next write
-    uint32_t flo = 0, fhi = 0;                          // 64-bit membership filter of this step's new entries
+    uint32_t filt = 0;                                  // 32-bit membership filter of this step's new entries
     uint32_t d = 0;                                     // start-DFA state: 0 = A not active yet, 1 = A alone
     uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;            // remaining bytes of the current 16-byte chunk, next byte in b0[7:0]
     uint4 pre = make_uint4(0, 0, 0, 0);                 // the chunk after it
@@ -201,7 +201,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             if (have) {   // ---- close step k: current <= next (Design/FPGA.v:733-737) ----
                 P0 |= Pn0; Pn0 = 0;
                 if (W == 2) { P1 |= Pn1; Pn1 = 0; }
-                re = wp; flo = 0; fhi = 0;
+                re = wp; filt = 0;
                 k++;
                 if (ovf) {   // the ring filled up while S_{k} was being built: S_{k-1} was fully examined, the general
                              // kernel re-runs the stream and reports from step k on
@@ -233,7 +233,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     const unsigned int need = sid / batch.chunk_streams + 1u;
                     while (*reinterpret_cast<const volatile unsigned int *>(batch.ready) < need) __nanosleep(256);
                 }
-                P0 = 0; P1 = 0; Pn0 = 0; Pn1 = 0; rp = 0; re = 0; wp = 0; flo = 0; fhi = 0; d = 0; k = 0;
+                P0 = 0; P1 = 0; Pn0 = 0; Pn1 = 0; rp = 0; re = 0; wp = 0; filt = 0; d = 0; k = 0;
                 if (batch.state_in) {   // resume: the stream's active set as left by an earlier call
                     const unsigned int *stt = batch.state_in + (size_t)sid * (1u + batch.state_cap);
                     const uint32_t ns = min(stt[0], batch.state_cap);
@@ -328,7 +328,8 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     const uint32_t tl = __ldg(nfa.dfa_act + x);
                     t = tl & 0x7FFFu;
                     x = (tl & 0x8000u) ? x + 1 : NONE;
-                } else if (rp != re) {                            // a member of S_k
+                } else
+                if (rp != re) {                            // a member of S_k
                     const uint32_t u = ring_ld(lb + rp);
                     rp = (rp + ROW) & RMASK;
                     idx = u + (u >= gbase ? hc : 0u);
@@ -365,14 +366,13 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     if (W == 1 || t < 64) Pn0 |= sb; else Pn1 |= sb;
                 } else {
                     const uint32_t fb = 1u << (t & 31);
-                    const bool fh = (t & 32) != 0;
-                    if (!(((fh ? fhi : flo) & fb) && ring_contains(lb, re, wp, ROW, RMASK, t))) {
+                    if (!((filt & fb) && ring_contains(lb, re, wp, ROW, RMASK, t))) {
                         const uint32_t nw = (wp + ROW) & RMASK;
                         if (nw == rp) ovf = true;                 // ring full: hand the stream to the general kernel
                         else {
                             ring_st(lb + wp, t);
                             wp = nw;
-                            if (fh) fhi |= fb; else flo |= fb;
+                            filt |= fb;
                         }
                     }
                 }

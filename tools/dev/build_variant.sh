@@ -4,7 +4,7 @@
 set -e
 cd "$(dirname "$0")/../../regex_fpga_b200/csrc"
 name=$1; shift
-make -s >/dev/null
+make -s >/dev/null 2>&1
 mkdir -p ../lib/variants
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC "$@" -c scan.cu -o ../lib/variants/scan_$name.o
 objs=$(ls ../lib/*.o | grep -v '/scan.o')
