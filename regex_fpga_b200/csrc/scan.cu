@@ -328,8 +328,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     const uint32_t tl = __ldg(nfa.dfa_act + x);
                     t = tl & 0x7FFFu;
                     x = (tl & 0x8000u) ? x + 1 : NONE;
-                } else
-                if (rp != re) {                            // a member of S_k
+                } else if (rp != re) {                            // a member of S_k
                     const uint32_t u = ring_ld(lb + rp);
                     rp = (rp + ROW) & RMASK;
                     idx = u + (u >= gbase ? hc : 0u);

@@ -20,7 +20,7 @@ def build_entries(rows):
 
 
 def random_nfa(rng, n_states=40, alphabet=8, p_accept=0.15, p_sticky=0.1, p_branch=0.3, max_fanout=3,
-               wide_classes=True):
+               wide_classes=True, unanchored=False):
     """Mix of the structures the shipped rulesets have: chains on symbol pairs, branching tries, class
     edges, self-loops on (nearly) all symbols, zero-out-degree accept states, same-symbol multi-target."""
     syms = rng.choice(256, size=alphabet, replace=False)
@@ -58,6 +58,15 @@ def random_nfa(rng, n_states=40, alphabet=8, p_accept=0.15, p_sticky=0.1, p_bran
     # state 0: start; make sure something is reachable
     if not rows[0]:
         rows[0] = [(int(rng.choice(syms)), 1)]
+    if unanchored and n_states >= 3:
+        # the shape of the shipped rulesets: state 0 enters a ".*" state on every symbol; that state stays active
+        # for ever and starts every pattern (the library follows its successors with a start DFA)
+        rows[0] = [(c, 1) for c in range(256)]
+        rows[1] = [(c, 1) for c in range(256)]
+        for _ in range(int(rng.integers(2, 10))):
+            c = int(rng.choice(syms))
+            for _ in range(int(rng.integers(1, max_fanout + 1))):
+                rows[1].append((c, int(rng.integers(2, n_states))))
     return build_entries(rows), syms
 
 

@@ -98,6 +98,44 @@ def test_random_nfas_both_kernels(gpu_ctx, seed):
         check_against_oracle(nfa, E, n, data, length, flags)
 
 
+@pytest.mark.parametrize("budget", ["0", "24", "200", "16384"])
+@pytest.mark.parametrize("seed", range(6))
+def test_start_dfa_unanchored_random_nfas(gpu_ctx, seed, budget, monkeypatch):
+    """Unanchored NFAs (state 0 -> ".*" state on every symbol): the lane kernel follows the ordinary successors of
+    the always-active state with a start DFA.  RFB_DFA_STATES = 0 disables it, small budgets force the failure-link
+    fallback (transitions beyond the budget continue from a shorter history and insert the rest explicitly).
+    Every variant must equal oracle B, one-shot and split into two resumed calls."""
+    monkeypatch.setenv("RFB_DFA_STATES", budget)
+    rng = np.random.default_rng(9100 + seed)
+    (E, n), syms = random_nfa(rng, n_states=int(rng.integers(12, 300)), alphabet=int(rng.integers(3, 12)),
+                              p_sticky=float(rng.choice([0.0, 0.05, 0.2])), max_fanout=int(rng.integers(1, 4)),
+                              unanchored=True)
+    nfa = gpu_ctx.nfa_from_entries(E, n)
+    assert nfa.info["image_ok"] == 1
+    length = int(rng.integers(40, 260))
+    data = random_streams(rng, syms, int(rng.integers(8, 120)), length)
+    whole = check_against_oracle(nfa, E, n, data, length, R.SCAN_SORT_RECORDS)
+    cut = length // 2
+    a = nfa.scan(np.ascontiguousarray(data[:, :cut]), data.shape[0], n_steps=cut, stride=cut, want_state=True, state_cap=255)
+    b = nfa.scan(np.ascontiguousarray(data[:, cut:]), data.shape[0], n_steps=length - cut, stride=length - cut,
+                 state_in=a.state, pos_base=cut)
+    if not np.any(a.state[:, 0] == R.STATE_OVERFLOW):
+        assert sorted(recs_tuple(a.records) + recs_tuple(b.records)) == recs_tuple(whole.records)
+        for s in range(min(8, data.shape[0])):     # exported sets hold every member exactly once
+            ids = a.state[s, 1:1 + a.state[s, 0]]
+            assert len(set(ids.tolist())) == len(ids)
+
+
+@pytest.mark.parametrize("name", ["snort_16", "l7_filter"])
+def test_start_dfa_budget_on_shipped_rulesets(gpu_ctx, snort, l7, name, monkeypatch):
+    """The shipped images with a start DFA cut at 300 states (most rows resolve through failure links)."""
+    rs = snort if name == "snort_16" else l7
+    monkeypatch.setenv("RFB_DFA_STATES", "300")
+    nfa = gpu_ctx.nfa_from_entries(rs.entries)
+    data = WL.make_batch_numpy("wmix", rs.lo, rs.hi, 64, 1500, 1536, seed=0x5EED0044)
+    check_against_oracle(nfa, rs.entries, rs.n_states, data, 1500, R.SCAN_SORT_RECORDS, stride=1536)
+
+
 def test_high_activity_overflows_to_warp_kernel(gpu_ctx):
     """More simultaneously active transient states than the lane kernel's ring holds: those streams
     must be re-run by the general kernel and still be bit-exact, with no double reports."""

@@ -128,3 +128,18 @@ def test_hypothesis_random_nfas_verify():
         assert info["n_states"] == n and info["image_ok"] == 1
 
     check()
+
+
+@pytest.mark.parametrize("budget", ["0", "16", "150", "16384"])
+def test_start_dfa_verifies_at_every_budget(snort, l7, budget, monkeypatch):
+    """image_build proves the start DFA against the CSR for every (DFA state, symbol) before it accepts the image
+    (image_verify): complete DFAs, DFAs cut at a small budget (failure-link fallback rows) and no DFA at all."""
+    monkeypatch.setenv("RFB_DFA_STATES", budget)
+    for rs in (snort, l7):
+        info = R.image_check(rs.entries)
+        assert info["image_ok"] == 1
+    rng = np.random.default_rng(31)
+    for _ in range(12):
+        (E, n), _ = random_nfa(rng, n_states=int(rng.integers(3, 200)), alphabet=int(rng.integers(2, 12)),
+                               p_sticky=0.1, unanchored=True)
+        assert R.image_check(E, n)["image_ok"] == 1
