@@ -229,6 +229,9 @@ def ours_arm(args, rank, world, local_rank):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION) goes to stderr's level
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(dev))
     E, n_states, lo, hi = load_ruleset(args.ruleset)
     ctx = R.Context(local_rank)
