@@ -159,6 +159,19 @@ void rfb_free(void *p);
  * but needs the general warp kernel, e.g. tables too large for shared memory). */
 int rfb_image_check(const uint32_t *entries, size_t n_entries, int64_t n_states, int sticky_words,
                     int bucket_bits, rfb_nfa_info *info);
+/* ---- execution-image files ------------------------------------------------
+ * The load-time re-indexing as an on-disk artefact: the BRAM image as loaded plus the tables the
+ * lane kernel runs on (per part, for an NFA that is cut into parts), layout documented in
+ * regex_fpga_b200/csrc/imagefile.cpp and DESIGN.md.  Saving skips nothing on the way back: loading
+ * checks the checksum, bounds, the structure of every table, and then proves the tables equivalent
+ * to the CSR exactly as a freshly built image is proven (RFB_E_FORMAT otherwise).  What loading
+ * saves is the table construction (hash search, start-DFA subset construction).
+ *   rfb_nfa_save_image / rfb_nfa_load_image : from / to an NFA resident on a context's GPU
+ *   rfb_image_file_build / rfb_image_file_check : host-only (no GPU): build and write, read and verify */
+int rfb_nfa_save_image(const rfb_nfa *nfa, const char *path);
+int rfb_nfa_load_image(rfb_ctx *ctx, const char *path, rfb_nfa **out);
+int rfb_image_file_build(const uint32_t *entries, size_t n_entries, int64_t n_states, const char *path);
+int rfb_image_file_check(const char *path, rfb_nfa_info *info);
 /* Number of symbol steps the testbench executes on an M-entry trace: M-1 (the last entry is loaded
  * but never processed and the final set is never examined; testbench_BLK_Mem.sv:71-86). */
 uint32_t rfb_tb_steps(uint32_t trace_entries);

@@ -5,8 +5,9 @@ include/regex_fpga_b200.h; this package is the thin ctypes mirror of that ABI.
 """
 from .engine import (Context, Nfa, RfbError, ScanResult, MATCH_DTYPE, SCAN_SORT_RECORDS, SCAN_FORCE_WARP,
                      SCAN_NO_COUNTS, SCAN_ASYNC, SCAN_ACCUMULATE, STATE_OVERFLOW, coe_parse, coe_write, coe_detect_size,
-                     trace_load_mem, trace_write_mem, tb_steps, image_check)
+                     trace_load_mem, trace_write_mem, tb_steps, image_check, image_file_build,
+                     image_file_check)
 
 __all__ = ["Context", "Nfa", "RfbError", "ScanResult", "MATCH_DTYPE", "SCAN_SORT_RECORDS", "SCAN_FORCE_WARP",
            "SCAN_NO_COUNTS", "SCAN_ASYNC", "SCAN_ACCUMULATE", "STATE_OVERFLOW", "coe_parse", "coe_write", "coe_detect_size",
-           "trace_load_mem", "trace_write_mem", "tb_steps", "image_check"]
+           "trace_load_mem", "trace_write_mem", "tb_steps", "image_check", "image_file_build", "image_file_check"]

@@ -50,6 +50,10 @@ SIGNATURES = {
     "rfb_coe_detect_size": (C.c_int64, [_U32P, C.c_size_t]),
     "rfb_free": (None, [_VP]),
     "rfb_image_check": (C.c_int, [_U32P, C.c_size_t, C.c_int64, C.c_int, C.c_int, C.POINTER(rfb_nfa_info)]),
+    "rfb_nfa_save_image": (C.c_int, [_VP, C.c_char_p]),
+    "rfb_nfa_load_image": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP)]),
+    "rfb_image_file_build": (C.c_int, [_U32P, C.c_size_t, C.c_int64, C.c_char_p]),
+    "rfb_image_file_check": (C.c_int, [C.c_char_p, C.POINTER(rfb_nfa_info)]),
     "rfb_tb_steps": (C.c_uint32, [C.c_uint32]),
     "rfb_scan": (C.c_int, [_VP, _VP, C.POINTER(rfb_batch), C.c_uint32, C.POINTER(rfb_result)]),
     "rfb_scan_device": (C.c_int, [_VP, _VP, C.POINTER(rfb_batch), C.c_uint32, _VP, C.POINTER(rfb_result)]),

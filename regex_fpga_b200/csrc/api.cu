@@ -245,50 +245,23 @@ static int upload_part(rfb_ctx *ctx, Part &p, uint32_t n_states_full, std::strin
     return RFB_OK;
 }
 
-int rfb_nfa_from_entries(rfb_ctx *ctx, const uint32_t *entries, size_t n_entries, int64_t n_states, rfb_nfa **out) {
-    if (!ctx || !out || !entries) return fail(ctx, RFB_E_INVALID, "NULL argument");
-    *out = nullptr;
+// Uploads a scan plan (imagefile.cpp) to the context's GPU.
+static int nfa_from_plan(rfb_ctx *ctx, Plan &plan, rfb_nfa **out) {
     rfb_nfa *nfa = new (std::nothrow) rfb_nfa();
     if (!nfa) return fail(ctx, RFB_E_NOMEM, "out of host memory");
     nfa->ctx = ctx;
     nfa->device = ctx->device;
-    std::string err;
-    int rc = nfa_from_entries(entries, n_entries, n_states, nfa->host, err);
-    if (rc) { delete nfa; return fail(ctx, rc, err); }
-    const ImageOptions opt = default_image_options();
-    cudaSetDevice(ctx->device);
-
-    // the whole NFA as one part if its tables fit one SM; otherwise groups of connected components, each with
-    // tables that fit; if it cannot be split, one part served by the general kernel
-    nfa->parts.resize(1);
-    nfa->parts[0].sub = nfa->host;
-    rc = image_build(nfa->host, opt, nfa->parts[0].img, err);
-    if (rc) { delete nfa; return fail(ctx, rc, err); }
-    if (!nfa->parts[0].img.ok && !std::getenv("RFB_NO_SPLIT")) {
-        // Prefer the coarsest cut whose parts all get full-quality tables (>= 8 buckets per branching state, every
-        // self-looping state in the mask): such a part runs at the speed of a small NFA, and a part that misses
-        // either costs far more than one extra pass over the batch.  Otherwise the coarsest cut that fits at all.
-        std::vector<Part> fallback;
-        for (uint32_t limit = 24000; limit >= 1500; limit /= 2) {
-            std::vector<std::vector<uint32_t>> groups;
-            nfa_components(nfa->host, limit, groups);
-            if (groups.empty()) break;
-            std::vector<Part> parts(groups.size());
-            bool all_ok = true, all_good = true;
-            for (size_t g = 0; g < groups.size() && rc == RFB_OK; g++) {
-                rc = nfa_extract(nfa->host, groups[g], parts[g].sub, parts[g].to_orig, err);
-                if (rc == RFB_OK) rc = image_build(parts[g].sub, opt, parts[g].img, err);
-                all_ok = all_ok && parts[g].img.ok;
-                all_good = all_good && parts[g].img.ok && parts[g].img.h.bucket_bits >= 3 && parts[g].img.n_sticky_dropped == 0;
-            }
-            if (rc) { delete nfa; return fail(ctx, rc, err); }
-            if (all_good) { nfa->parts.swap(parts); fallback.clear(); break; }
-            if (all_ok && fallback.empty()) fallback.swap(parts);
-        }
-        if (!fallback.empty()) nfa->parts.swap(fallback);
+    nfa->host = std::move(plan.host);
+    nfa->parts.resize(plan.parts.size());
+    for (size_t g = 0; g < plan.parts.size(); g++) {
+        nfa->parts[g].sub = std::move(plan.parts[g].sub);
+        nfa->parts[g].img = std::move(plan.parts[g].img);
+        nfa->parts[g].to_orig = std::move(plan.parts[g].to_orig);
     }
+    cudaSetDevice(ctx->device);
+    std::string err;
     for (Part &p : nfa->parts) {
-        rc = upload_part(ctx, p, nfa->host.n_states, err);
+        const int rc = upload_part(ctx, p, nfa->host.n_states, err);
         if (rc) { rfb_nfa_destroy(nfa); return rc == RFB_E_CUDA ? rc : fail(ctx, rc, err); }
     }
     if (nfa->parts.size() == 1) nfa->full = nfa->parts[0].dev;
@@ -304,6 +277,63 @@ int rfb_nfa_from_entries(rfb_ctx *ctx, const uint32_t *entries, size_t n_entries
         nfa->full.trans = nfa->d_full + nfa->host.n_states + 1;
     }
     *out = nfa;
+    return RFB_OK;
+}
+
+int rfb_nfa_from_entries(rfb_ctx *ctx, const uint32_t *entries, size_t n_entries, int64_t n_states, rfb_nfa **out) {
+    if (!ctx || !out || !entries) return fail(ctx, RFB_E_INVALID, "NULL argument");
+    *out = nullptr;
+    Plan plan;
+    std::string err;
+    const int rc = plan_build(entries, n_entries, n_states, default_image_options(), !std::getenv("RFB_NO_SPLIT"), plan, err);
+    if (rc) return fail(ctx, rc, err);
+    return nfa_from_plan(ctx, plan, out);
+}
+
+int rfb_nfa_load_image(rfb_ctx *ctx, const char *path, rfb_nfa **out) {
+    if (!ctx || !path || !out) return fail(ctx, RFB_E_INVALID, "NULL argument");
+    *out = nullptr;
+    Plan plan;
+    std::string err;
+    const int rc = plan_read(path, plan, err);
+    if (rc) return fail(ctx, rc, err);
+    return nfa_from_plan(ctx, plan, out);
+}
+
+int rfb_nfa_save_image(const rfb_nfa *nfa, const char *path) {
+    if (!nfa || !path) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    Plan plan;
+    plan.host = nfa->host;
+    plan.parts.resize(nfa->parts.size());
+    for (size_t g = 0; g < nfa->parts.size(); g++) {
+        plan.parts[g].img = nfa->parts[g].img;
+        plan.parts[g].to_orig = nfa->parts[g].to_orig;
+    }
+    std::string err;
+    const int rc = plan_write(plan, path, err);
+    return rc ? fail(nfa->ctx, rc, err) : RFB_OK;
+}
+
+int rfb_image_file_build(const uint32_t *entries, size_t n_entries, int64_t n_states, const char *path) {
+    if (!entries || !path) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    Plan plan;
+    std::string err;
+    int rc = plan_build(entries, n_entries, n_states, default_image_options(), !std::getenv("RFB_NO_SPLIT"), plan, err);
+    if (rc == RFB_OK) rc = plan_write(plan, path, err);
+    return rc ? fail(nullptr, rc, err) : RFB_OK;
+}
+
+int rfb_image_file_check(const char *path, rfb_nfa_info *info) {
+    if (!path || !info) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    Plan plan;
+    std::string err;
+    const int rc = plan_read(path, plan, err);
+    if (rc) return fail(nullptr, rc, err);
+    fill_info(plan.host, plan.parts[0].img, info);
+    bool all_ok = true;
+    for (const PlanPart &p : plan.parts) all_ok = all_ok && p.img.ok;
+    info->image_ok = all_ok ? 1u : 0u;
+    info->n_parts = (uint32_t)plan.parts.size();
     return RFB_OK;
 }
 

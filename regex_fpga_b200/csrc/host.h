@@ -133,4 +133,24 @@ void image_successors(const Image &img, uint32_t s, uint32_t c, std::vector<uint
 // Exhaustive equivalence check image == CSR.  Returns 0 or RFB_E_INTERNAL with a message.
 int image_verify(const Nfa &nfa, const Image &img, std::string &err);
 
+// ---- imagefile.cpp ----------------------------------------------------------------------------
+// The scan plan of an NFA: the NFA as loaded and its parts (one, or several when the whole NFA's tables do not fit
+// one SM), each with its execution image.  plan_write / plan_read are the on-disk form (layout in imagefile.cpp);
+// plan_read trusts nothing: checksum, bounds, image_validate_structure() and image_verify() for every part.
+struct PlanPart {
+    Nfa sub;                           // the part as an NFA of its own (state 0 + the part's states)
+    Image img;
+    std::vector<uint32_t> to_orig;     // sub state id -> reference state id (empty: identity)
+};
+struct Plan {
+    Nfa host;
+    std::vector<PlanPart> parts;       // >= 1
+};
+int plan_build(const uint32_t *entries, size_t n_entries, int64_t n_states, const ImageOptions &opt, bool allow_split,
+               Plan &plan, std::string &err);
+int plan_write(const Plan &plan, const std::string &path, std::string &err);
+int plan_read(const std::string &path, Plan &plan, std::string &err);
+// every index an interpreter of the tables can follow stays inside them (run before image_verify on untrusted input)
+int image_validate_structure(const Image &img, uint32_t n_states, std::string &err);
+
 }  // namespace rfb

@@ -533,6 +533,19 @@ int image_verify(const Nfa &nfa, const Image &img, std::string &err) {
             }
         }
     }
+    {   // what the kernel reads but image_successors() does not: the "attention" masks and the per-symbol hash
+        const ImageHeader &h = img.h;
+        const uint32_t W = h.sticky_words, mstride = 32u * W;
+        const uint32_t *cmap = reinterpret_cast<const uint32_t *>(&img.blob[h.off_cmap]);
+        for (uint32_t c = 0; c < 256; c++) {
+            const uint64_t *A = reinterpret_cast<const uint64_t *>(&img.blob[h.off_mask + c * mstride]);
+            const uint64_t *K = reinterpret_cast<const uint64_t *>(&img.blob[h.off_mask + c * mstride + 16]);
+            const uint64_t *M = K + W;
+            for (uint32_t w = 0; w < W; w++)
+                if (A[w] != (~K[w] | M[w])) { err = "sticky attention mask disagrees with K and M at symbol " + std::to_string(c); return RFB_E_INTERNAL; }
+            if ((cmap[c] >> 16) != (((c * h.hash_mul) >> h.hash_shift) & 0xFFu)) { err = "per-symbol hash disagrees with the header at symbol " + std::to_string(c); return RFB_E_INTERNAL; }
+        }
+    }
     if (img.h.accel) {
         // Start DFA: for every DFA state d >= 1 and every symbol c,
         //   members(next) + insertion list  ==  successors on c of members(d) and of A (A's self loop aside),

@@ -90,6 +90,19 @@ def image_check(entries, n_states=-1, sticky_words=0, bucket_bits=0):
     return _info_dict(info)
 
 
+def image_file_build(entries, path, n_states=-1):
+    """Host-only: build the scan plan (parts + execution images) of an NFA and write it as an image file."""
+    e = np.ascontiguousarray(entries, dtype=np.uint32)
+    _check(_lib.load().rfb_image_file_build(e.ctypes.data_as(C.POINTER(C.c_uint32)), e.size, n_states, str(path).encode()))
+
+
+def image_file_check(path):
+    """Host-only: read an image file and verify every table against the CSR it carries; returns the info dict."""
+    info = rfb_nfa_info()
+    _check(_lib.load().rfb_image_file_check(str(path).encode(), C.byref(info)))
+    return _info_dict(info)
+
+
 # ---- GPU objects -----------------------------------------------------------------------------------
 class Context:
     """One GPU (one process per GPU).  Fails loudly when no CUDA device is usable."""
@@ -124,6 +137,12 @@ class Context:
     def load_coe(self, path, n_states=-1):
         h = C.c_void_p()
         _check(self._L.rfb_nfa_load_coe(self._h, str(path).encode(), n_states, C.byref(h)), self._h)
+        return Nfa(self, h)
+
+    def load_image(self, path):
+        """An NFA from an execution-image file (Nfa.save_image / image_file_build): verified, not rebuilt."""
+        h = C.c_void_p()
+        _check(self._L.rfb_nfa_load_image(self._h, str(path).encode(), C.byref(h)), self._h)
         return Nfa(self, h)
 
     def nfa_from_entries(self, entries, n_states=-1):
@@ -181,6 +200,9 @@ class Nfa:
         return out
 
     # -- host buffers in, host results out (H2D + kernels + D2H inside the call) --
+    def save_image(self, path):
+        _check(self._L.rfb_nfa_save_image(self._h, str(path).encode()), self.ctx._h)
+
     def scan(self, data, n_streams, n_steps=0, stride=0, offsets=None, steps=None, record_capacity=1 << 20,
              flags=SCAN_SORT_RECORDS, stream_id_base=0, want_counts=True, state_in=None, want_state=False,
              state_cap=63, pos_base=0, records_out=None, counts_out=None):

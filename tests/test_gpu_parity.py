@@ -478,3 +478,32 @@ def test_large_batch_properties(gpu_ctx, snort):
     want = O.b_scan_many(snort.entries, snort.n_states, host, 512, 1536, 1500, want_recs=False)
     c_s, _ = run(torch.from_numpy(host).to("cuda:0"))
     assert np.array_equal(c_s.astype(np.uint64), want["counts"])
+
+
+def test_image_file_save_load_scan(gpu_ctx, snort, tmp_path):
+    """an NFA saved as an execution-image file and loaded back (verified, not rebuilt) scans
+    bit-identically; a multi-part NFA travels with its part table; a host-built file loads too."""
+    data = WL.make_batch_numpy("wmix", snort.lo, snort.hi, 96, 1500, 1536, seed=0x5EED0077)
+    nfa = gpu_ctx.nfa_from_entries(snort.entries)
+    want = nfa.scan(data, 96, n_steps=1500, stride=1536)
+    p = tmp_path / "snort.rfbimg"
+    nfa.save_image(p)
+    again = gpu_ctx.load_image(p)
+    assert again.info == nfa.info
+    got = again.scan(data, 96, n_steps=1500, stride=1536)
+    assert recs_tuple(got.records) == recs_tuple(want.records) and np.array_equal(got.counts, want.counts)
+    q = tmp_path / "host.rfbimg"
+    R.image_file_build(snort.entries, q)
+    assert q.read_bytes() == p.read_bytes()                       # the file is a function of the NFA alone
+    E3, n3 = WL.replicate_nfa(snort.entries, snort.n_states, 3)
+    big = gpu_ctx.nfa_from_entries(E3, n3)
+    assert big.info["n_parts"] >= 2
+    r3 = tmp_path / "x3.rfbimg"
+    big.save_image(r3)
+    big2 = gpu_ctx.load_image(r3)
+    assert big2.info == big.info
+    a = big.scan(data[:32], 32, n_steps=1500, stride=1536)
+    b = big2.scan(data[:32], 32, n_steps=1500, stride=1536)
+    assert recs_tuple(a.records) == recs_tuple(b.records) and a.n_matches == 3 * nfa.scan(data[:32], 32, n_steps=1500, stride=1536).n_matches
+    with pytest.raises(R.RfbError):
+        gpu_ctx.load_image(tmp_path / "missing.rfbimg")
