@@ -178,7 +178,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     // of a firing sticky state) with one edge-table lookup and one insertion.  Lanes of a warp are at different
     // symbols and different streams; a lane that finishes a stream takes the next one from a global counter, so
     // busy and quiet streams balance automatically.
-    uint64_t P0 = 0, P1 = 0, Pn0 = 0, Pn1 = 0;          // sticky sets (P1/Pn1 unused when W == 1)
+    uint64_t P0 = 0, P1 = 0;                            // sticky set (P1 unused when W == 1)
     uint32_t rp = 0, re = 0, wp = 0;                    // ring byte offsets: next read, end of current set, next write
     uint32_t filt = 0;                                  // 32-bit membership filter of this step's new entries
     uint32_t d = 0;                                     // start-DFA state: 0 = A not active yet, 1 = A alone
@@ -199,8 +199,6 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
 #pragma unroll 1
         for (int rep = 0; rep < open_reps && !pend; rep++) {
             if (have) {   // ---- close step k: current <= next (Design/FPGA.v:733-737) ----
-                P0 |= Pn0; Pn0 = 0;
-                if (W == 2) { P1 |= Pn1; Pn1 = 0; }
                 re = wp; filt = 0;
                 k++;
                 if (ovf) {   // the ring filled up while S_{k} was being built: S_{k-1} was fully examined, the general
@@ -233,7 +231,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     const unsigned int need = sid / batch.chunk_streams + 1u;
                     while (*reinterpret_cast<const volatile unsigned int *>(batch.ready) < need) __nanosleep(256);
                 }
-                P0 = 0; P1 = 0; Pn0 = 0; Pn1 = 0; rp = 0; re = 0; wp = 0; filt = 0; d = 0; k = 0;
+                P0 = 0; P1 = 0; rp = 0; re = 0; wp = 0; filt = 0; d = 0; k = 0;
                 if (batch.state_in) {   // resume: the stream's active set as left by an earlier call
                     const unsigned int *stt = batch.state_in + (size_t)sid * (1u + batch.state_cap);
                     const uint32_t ns = min(stt[0], batch.state_cap);
@@ -362,7 +360,9 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             if (hit && !ovf) {   // ---- the one insertion site: add t to S_{k+1} ----
                 if (t < nsb) {                                    // entering a sticky state
                     const uint64_t sb = 1ull << (t & 63);
-                    if (W == 1 || t < 64) Pn0 |= sb; else Pn1 |= sb;
+                    // P is read only when a step opens (survivors, firing bits) and insertions happen after that:
+                    // a state entered now is first seen by the next step, as it must be
+                    if (W == 1 || t < 64) P0 |= sb; else P1 |= sb;
                 } else {
                     const uint32_t fb = 1u << (t & 31);
                     if (!((filt & fb) && ring_contains(lb, re, wp, ROW, RMASK, t))) {
