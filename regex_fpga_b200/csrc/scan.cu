@@ -173,8 +173,8 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     constexpr uint32_t MSTRIDE = 32u * W;
 
     // One THREAD per stream, and every thread walks its stream at its own pace: the loop below is flat.  An
-    // iteration either opens the next symbol step of the lane's stream (symbol fetch, two-symbol table, sticky
-    // masks) or drains ONE work item of the open step (a two-symbol-table hit, a member of the current set, a row
+    // iteration either opens the next symbol step of the lane's stream (symbol fetch, start-DFA step, sticky
+    // masks) or drains ONE work item of the open step (a start-DFA insertion, a member of the current set, a row
     // of a firing sticky state) with one edge-table lookup and one insertion.  Lanes of a warp are at different
     // symbols and different streams; a lane that finishes a stream takes the next one from a global counter, so
     // busy and quiet streams balance automatically.
