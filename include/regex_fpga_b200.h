@@ -159,6 +159,11 @@ void rfb_free(void *p);
  * but needs the general warp kernel, e.g. tables too large for shared memory). */
 int rfb_image_check(const uint32_t *entries, size_t n_entries, int64_t n_states, int sticky_words,
                     int bucket_bits, rfb_nfa_info *info);
+/* One line of text per part describing how the NFA will be scanned (tables, sticky states, start DFA:
+ * states, symbol classes, states beyond the budget, insertion-list entries).  Writes at most cap bytes
+ * including the terminator; returns RFB_OK, or RFB_E_INVALID if cap is too small. */
+int rfb_nfa_describe(const rfb_nfa *nfa, char *buf, size_t cap);
+
 /* ---- execution-image files ------------------------------------------------
  * The load-time re-indexing as an on-disk artefact: the BRAM image as loaded plus the tables the
  * lane kernel runs on (per part, for an NFA that is cut into parts), layout documented in

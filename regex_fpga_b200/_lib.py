@@ -50,6 +50,7 @@ SIGNATURES = {
     "rfb_coe_detect_size": (C.c_int64, [_U32P, C.c_size_t]),
     "rfb_free": (None, [_VP]),
     "rfb_image_check": (C.c_int, [_U32P, C.c_size_t, C.c_int64, C.c_int, C.c_int, C.POINTER(rfb_nfa_info)]),
+    "rfb_nfa_describe": (C.c_int, [_VP, C.c_char_p, C.c_size_t]),
     "rfb_nfa_save_image": (C.c_int, [_VP, C.c_char_p]),
     "rfb_nfa_load_image": (C.c_int, [_VP, C.c_char_p, C.POINTER(_VP)]),
     "rfb_image_file_build": (C.c_int, [_U32P, C.c_size_t, C.c_int64, C.c_char_p]),

@@ -364,6 +364,28 @@ int rfb_nfa_get_info(const rfb_nfa *nfa, rfb_nfa_info *info) {
     return RFB_OK;
 }
 
+int rfb_nfa_describe(const rfb_nfa *nfa, char *buf, size_t cap) {
+    if (!nfa || !buf) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    std::string s;
+    for (size_t g = 0; g < nfa->parts.size(); g++) {
+        const Part &p = nfa->parts[g];
+        char line[512];
+        if (p.img.ok)
+            std::snprintf(line, sizeof line,
+                          "part %zu: states %u kernel lane image_bytes %u slots %u bucket_bits %u sticky %u sticky_dropped %u "
+                          "dfa %u dfa_states %u dfa_classes %u dfa_beyond_budget %u dfa_list_entries %zu\n",
+                          g, p.sub.n_states, p.img.h.blob_bytes, p.img.h.n_slots, p.img.h.bucket_bits, p.img.n_sticky,
+                          p.img.n_sticky_dropped, p.img.h.accel, p.img.dfa.n, p.img.dfa.ncls, p.img.dfa.n_frontier,
+                          p.img.dfa.act.size());
+        else
+            std::snprintf(line, sizeof line, "part %zu: states %u kernel general (%s)\n", g, p.sub.n_states, p.img.why_not.c_str());
+        s += line;
+    }
+    if (s.size() + 1 > cap) return fail(nfa->ctx, RFB_E_INVALID, "buffer too small");
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return RFB_OK;
+}
+
 int rfb_image_check(const uint32_t *entries, size_t n_entries, int64_t n_states, int sticky_words, int bucket_bits,
                     rfb_nfa_info *info) {
     if (!entries || !info) return fail(nullptr, RFB_E_INVALID, "NULL argument");

@@ -329,11 +329,14 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
             D.act.assign(1, 0);                                // index 0: unused
             D.n_frontier = 0;
             bool act_overflow = false;
+            uint64_t work = 0;                                 // edge-list visits so far: bounds the load time on NFAs whose subsets explode
+            const uint64_t WORK_CAP = 60ull * 1000 * 1000;
             std::vector<uint32_t> T, ord;
             std::vector<uint16_t> lst;
             for (uint32_t d = 1; d < members.size() && !act_overflow; d++) {
                 if (D.dt.size() < (size_t)(d + 1) * ncls) { D.dt.resize((size_t)(d + 1) * ncls, 0); D.dta.resize((size_t)(d + 1) * ncls, 0); }
                 bool fell_back = false;
+                work += (uint64_t)ncls * (members[d].size() + 1);
                 for (uint32_t q = 0; q < ncls; q++) {
                     const uint32_t c = rep[q];
                     T.clear();
@@ -346,7 +349,7 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
                     uint32_t nd;
                     auto it = id_of.find(ord);
                     if (it != id_of.end()) nd = it->second;
-                    else if (members.size() < budget) {
+                    else if (members.size() < budget && work < WORK_CAP) {
                         nd = (uint32_t)members.size();
                         id_of.emplace(ord, nd);
                         members.push_back(ord);

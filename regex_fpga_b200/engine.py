@@ -200,6 +200,12 @@ class Nfa:
         return out
 
     # -- host buffers in, host results out (H2D + kernels + D2H inside the call) --
+    def describe(self):
+        """One line per part: kernel, table sizes, sticky states, start-DFA size (rfb_nfa_describe)."""
+        buf = C.create_string_buffer(1 << 16)
+        _check(self._L.rfb_nfa_describe(self._h, buf, len(buf)), self.ctx._h)
+        return buf.value.decode()
+
     def save_image(self, path):
         _check(self._L.rfb_nfa_save_image(self._h, str(path).encode()), self.ctx._h)
 

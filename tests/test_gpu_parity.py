@@ -480,6 +480,17 @@ def test_large_batch_properties(gpu_ctx, snort):
     assert np.array_equal(c_s.astype(np.uint64), want["counts"])
 
 
+def test_describe_reports_the_start_dfa(gpu_ctx, snort, l7, monkeypatch):
+    for rs, states in ((snort, 8495), (l7, 1763)):
+        text = gpu_ctx.nfa_from_entries(rs.entries).describe()
+        assert "kernel lane" in text and f"dfa_states {states} " in text and "dfa_beyond_budget 0 " in text   # complete DFAs
+    monkeypatch.setenv("RFB_DFA_STATES", "300")
+    text = gpu_ctx.nfa_from_entries(snort.entries).describe()
+    assert "dfa_states 300 " in text and "dfa_beyond_budget 0 " not in text
+    monkeypatch.setenv("RFB_DFA_STATES", "0")
+    assert "dfa 0 " in gpu_ctx.nfa_from_entries(snort.entries).describe()
+
+
 def test_image_file_save_load_scan(gpu_ctx, snort, tmp_path):
     """an NFA saved as an execution-image file and loaded back (verified, not rebuilt) scans
     bit-identically; a multi-part NFA travels with its part table; a host-built file loads too."""

@@ -143,3 +143,19 @@ def test_start_dfa_verifies_at_every_budget(snort, l7, budget, monkeypatch):
         (E, n), _ = random_nfa(rng, n_states=int(rng.integers(3, 200)), alphabet=int(rng.integers(2, 12)),
                                p_sticky=0.1, unanchored=True)
         assert R.image_check(E, n)["image_ok"] == 1
+
+
+def test_start_dfa_build_is_bounded_when_subsets_explode():
+    """600 states over a 4-letter alphabet with random back edges: the subset construction would run away; the
+    builder stops creating DFA states at a work bound and resolves the rest through failure links."""
+    import time
+    rng = np.random.default_rng(3)
+    n = 600
+    rows = [[(c, 1) for c in range(256)],
+            [(c, 1) for c in range(256)] + [(int(rng.integers(97, 101)), int(rng.integers(2, n))) for _ in range(40)]]
+    for _ in range(2, n):
+        rows.append([(int(rng.integers(97, 101)), int(rng.integers(2, n))) for _ in range(4)])
+    E, nn = build_entries(rows)
+    t0 = time.time()
+    info = R.image_check(E, nn)
+    assert info["image_ok"] == 1 and time.time() - t0 < 60
