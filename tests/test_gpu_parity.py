@@ -478,6 +478,17 @@ def test_large_batch_properties(gpu_ctx, snort):
     want = O.b_scan_many(snort.entries, snort.n_states, host, 512, 1536, 1500, want_recs=False)
     c_s, _ = run(torch.from_numpy(host).to("cuda:0"))
     assert np.array_equal(c_s.astype(np.uint64), want["counts"])
+    # the full per-state count vector of a 32 768-stream block against the multi-threaded oracle, and
+    # the records of the first 4 096 + 4 096 strided streams
+    blk = dev[: 1 << 15].contiguous()
+    c_blk, m_blk = run(blk)
+    want = O.b_scan_many(snort.entries, snort.n_states, blk.cpu().numpy(), 1 << 15, 1536, 1500, want_recs=False)
+    assert np.array_equal(c_blk.astype(np.uint64), want["counts"]) and m_blk == int(want["counts"].sum())
+    idx = np.concatenate([np.arange(4096), np.arange(4096, n, (n - 4096) // 4096)[:4096]])
+    host = dev[torch.from_numpy(idx).to("cuda:0")].cpu().numpy()
+    got = nfa.scan(host, host.shape[0], n_steps=1500, stride=1536, record_capacity=1 << 20)
+    want = O.b_scan_many(snort.entries, snort.n_states, host, host.shape[0], 1536, 1500, cap=1 << 20)
+    assert got.n_dropped == 0 and recs_tuple(got.records) == recs_tuple(want["recs"])
 
 
 def test_describe_reports_the_start_dfa(gpu_ctx, snort, l7, monkeypatch):
