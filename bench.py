@@ -217,6 +217,24 @@ def run_e2e(args, torch, dist, nfa, batch, n, first, cap, n_states, n_matches, b
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_cpus(local_rank):
+    """Multi-GPU runs: pin this rank to the CPUs next to its GPU (NVML's affinity mask) before any pinned host memory
+    is allocated, so that the e2e leg's H2D copies read memory of the GPU's own NUMA node.  Best effort."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def ours_arm(args, rank, world, local_rank):
     import torch
     import regex_fpga_b200 as R
@@ -226,6 +244,7 @@ def ours_arm(args, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device -- the scan has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
+    numa = bind_to_gpu_cpus(local_rank) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -304,7 +323,8 @@ def ours_arm(args, rank, world, local_rank):
         line = {
             "metric": metric_name(args), "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload_config(args, world),
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": dict(workload_config(args, world), **({"cpus_bound_per_rank": numa} if numa else {})),
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": 2 * args.steps,
