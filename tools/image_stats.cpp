@@ -94,6 +94,22 @@ int main(int argc, char **argv) {
             cur.swap(nxt); nxt.clear(); s.symbols++;
         }
     }
+    if (getenv("DUMP_STREAMS")) {   // per stream: class, explicit lookups, static firing-weight score (full / first 128 bytes)
+        for (int j = 0; j < n_streams; j++) {
+            const std::vector<uint8_t> &src = (j & 1) ? hi : lo;
+            uint64_t off = splitmix64(0x5EED0001ull ^ (uint64_t)j) % (std::min(lo.size(), hi.size()) - L + 1);
+            uint64_t look = 0, sc = 0, sc128 = 0;
+            for (uint32_t k = 0; k < L; k++) {
+                look += per_sym_lookups[j][k];
+                const uint32_t c = src[off + k];
+                const uint64_t *K = (const uint64_t *)&img.blob[h.off_mask + c * ms + 16];
+                const uint64_t *M = K + W;
+                uint32_t wgt = 0; for (uint32_t w = 0; w < W; w++) wgt += __builtin_popcountll(M[w]);
+                sc += wgt; if (k < 128) sc128 += wgt;
+            }
+            printf("S %d %d %llu %llu %llu\n", j, j & 1, (unsigned long long)look, (unsigned long long)sc, (unsigned long long)sc128);
+        }
+    }
     for (int t = 0; t < 2; t++) {
         Stats &s = st[t];
         printf("%s: per symbol: t2hits %.3f entries %.3f lookups %.3f indirect %.3f class %.3f pushes %.3f attn %.3f inj %.3f sticky %.2f maxlist %.0f\n", t ? "hi" : "lo", s.t2hits / s.symbols,
