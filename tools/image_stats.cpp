@@ -99,6 +99,16 @@ int main(int argc, char **argv) {
             const std::vector<uint8_t> &src = (j & 1) ? hi : lo;
             uint64_t off = splitmix64(0x5EED0001ull ^ (uint64_t)j) % (std::min(lo.size(), hi.size()) - L + 1);
             uint64_t look = 0, sc = 0, sc128 = 0;
+            uint32_t fl64 = 0, fl128 = 0, fl256 = 0, st64 = 0, st128 = 0, st256 = 0, dd = 1;   // DFA-only sniff: flagged transitions / sticky insertions in a prefix
+            { const uint32_t *cmap2 = (const uint32_t *)&img.blob[h.off_cmap]; const Image::Dfa &D = img.dfa;
+              for (uint32_t k = 0; k < 256 && h.accel; k++) {
+                const size_t at = (size_t)dd * D.ncls + (cmap2[src[off + k]] & 0xFF);
+                dd = D.dt[at] & 0x7FFF; if (dd == 0) dd = 1;
+                uint32_t nst = 0;
+                if (D.dt[at] & 0x8000) for (uint32_t q = D.dta[at];; q++) { if ((D.act[q] & 0x7FFFu) < h.nsb) nst++; if (!(D.act[q] & 0x8000)) break; }
+                const uint32_t f = (D.dt[at] >> 15) & 1;
+                if (k < 64) { fl64 += f; st64 += nst; } if (k < 128) { fl128 += f; st128 += nst; } fl256 += f; st256 += nst;
+              } }
             for (uint32_t k = 0; k < L; k++) {
                 look += per_sym_lookups[j][k];
                 const uint32_t c = src[off + k];
@@ -107,7 +117,7 @@ int main(int argc, char **argv) {
                 uint32_t wgt = 0; for (uint32_t w = 0; w < W; w++) wgt += __builtin_popcountll(M[w]);
                 sc += wgt; if (k < 128) sc128 += wgt;
             }
-            printf("S %d %d %llu %llu %llu\n", j, j & 1, (unsigned long long)look, (unsigned long long)sc, (unsigned long long)sc128);
+            printf("S %d %d %llu %llu %llu %u %u %u %u %u %u\n", j, j & 1, (unsigned long long)look, (unsigned long long)sc, (unsigned long long)sc128, fl64, fl128, fl256, st64, st128, st256);
         }
     }
     for (int t = 0; t < 2; t++) {
