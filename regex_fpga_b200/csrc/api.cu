@@ -525,6 +525,9 @@ static int enqueue_kernels(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b,
     od.counts = (flags & RFB_SCAN_NO_COUNTS) ? nullptr : reinterpret_cast<unsigned long long *>(res->counts);
     od.records = res->records; od.capacity = res->records ? res->record_capacity : 0;
     od.g = ctx->g; od.rescan = ctx->rescan;
+    // a row no kernel writes must read as "overflow", never as stale memory
+    if (b->state_out && b->n_streams)
+        CU(ctx, cudaMemsetAsync(b->state_out, 0xFF, (size_t)b->n_streams * (1 + (size_t)b->state_cap) * 4, st));
     if (b->n_streams) {
         bool first = true;
         for (const Part &p : nfa->parts) {   // one pass over the batch per part; reports of different parts are disjoint

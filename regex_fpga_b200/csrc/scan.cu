@@ -202,8 +202,9 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                 re = wp; filt = 0;
                 k++;
                 if (ovf) {   // the ring filled up while S_{k} was being built: S_{k-1} was fully examined, the general
-                             // kernel re-runs the stream and reports from step k on
-                    if (k < nsteps) {
+                             // kernel re-runs the stream and reports from step k on (after the last step there is
+                             // nothing left to report, but the caller may want S_{n_steps}: only that kernel has it)
+                    if (k < nsteps || batch.state_out) {
                         const unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
                         out.rescan[slot] = make_uint2(sid, k);
                     }

@@ -338,6 +338,28 @@ def test_resume_with_more_states_than_the_ring_holds(gpu_ctx):
     assert np.all(small.state[:, 0] == R.STATE_OVERFLOW)
 
 
+@pytest.mark.parametrize("seed", [500337, 500008, 500014, 500045])
+def test_resume_when_the_ring_overflows_in_the_last_step(gpu_ctx, seed):
+    """Regression (found by tools/dev/stress_parity.py): a stream whose ring filled up while S_{n_steps} was being
+    built had nothing left to report, so the lane kernel did not hand it over -- and nobody wrote its state_out row.
+    Now the general kernel re-runs it for the state, and rows start out as the overflow mark."""
+    rng = np.random.default_rng(seed)
+    rng.choice([0, 12, 40, 300, 16384])                              # same draw order as the soak tool
+    (E, n), syms = random_nfa(rng, n_states=int(rng.integers(3, 500)), alphabet=int(rng.integers(2, 20)),
+                              p_sticky=float(rng.choice([0.0, 0.05, 0.2, 0.4])), p_accept=float(rng.choice([0.05, 0.15, 0.3])),
+                              max_fanout=int(rng.integers(1, 5)), unanchored=bool(rng.integers(0, 4)))
+    L = int(rng.integers(2, 400)); ns = int(rng.integers(1, 150))
+    data = random_streams(rng, syms, ns, L, p_alpha=float(rng.choice([0.6, 0.85, 0.97])))
+    nfa = gpu_ctx.nfa_from_entries(E, n)
+    want = O.b_scan_many(E, n, data, ns, L, L, cap=1 << 22)
+    cut = L // 2
+    a = nfa.scan(np.ascontiguousarray(data[:, :cut]), ns, n_steps=cut, stride=cut, want_state=True, state_cap=255, record_capacity=1 << 22)
+    assert a.n_rescanned > 0 and not np.any(a.state[:, 0] == R.STATE_OVERFLOW)
+    b = nfa.scan(np.ascontiguousarray(data[:, cut:]), ns, n_steps=L - cut, stride=L - cut, state_in=a.state, pos_base=cut,
+                 record_capacity=1 << 22)
+    assert sorted(recs_tuple(a.records) + recs_tuple(b.records)) == recs_tuple(want["recs"])
+
+
 def test_config5_replicated_large_nfa_adversarial(gpu_ctx, snort):
     """BASELINE config 5: 7 x snort_16 behind one start state (66 592 states, beyond the FPGA's own 16-bit
     rd_address) with adversarial high-activity streams and hi-trace windows.  The tables of the whole NFA do not fit
