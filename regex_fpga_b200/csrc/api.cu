@@ -204,6 +204,7 @@ static int upload_part(rfb_ctx *ctx, Part &p, uint32_t n_states_full, std::strin
     UP(p.d_erec, ec.erec, unsigned long long);
     UP(p.d_emembs, ec.memb, uint32_t);
     p.dev.n_states = h.n_states;
+    p.dev.n_ref_states = n_states_full;
     p.dev.row_ptr = p.d_entries;
     p.dev.trans = p.d_entries + h.n_states + 1;
     p.dev.eptr = p.d_eptr; p.dev.erec = p.d_erec; p.dev.emembs = p.d_emembs;
@@ -273,6 +274,7 @@ static int nfa_from_plan(rfb_ctx *ctx, Plan &plan, rfb_nfa **out) {
             return cuda_fail(ctx, e, "upload CSR");
         }
         nfa->full.n_states = nfa->host.n_states;
+        nfa->full.n_ref_states = nfa->host.n_states;
         nfa->full.row_ptr = nfa->d_full;
         nfa->full.trans = nfa->d_full + nfa->host.n_states + 1;
     }
@@ -591,6 +593,14 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     if (nfa->ctx != ctx) return fail(ctx, RFB_E_INVALID, "nfa belongs to another context");
     int rc = check_batch(ctx, b, true);
     if (rc) return rc;
+    if (b->state_in)   // host rows can be checked: an overflow mark or a foreign id cannot be resumed
+        for (uint64_t s = 0; s < b->n_streams; s++) {
+            const unsigned int *row = b->state_in + s * (1 + (uint64_t)b->state_cap);
+            if (row[0] > b->state_cap)
+                return fail(ctx, RFB_E_INVALID, "state_in of stream " + std::to_string(s) + (row[0] == 0xFFFFFFFFu ? " is an overflow mark (RFB_STATE_OVERFLOW): that stream cannot be resumed" : " holds more than state_cap ids"));
+            for (unsigned int q = 0; q < row[0]; q++)
+                if (row[1 + q] >= nfa->host.n_states) return fail(ctx, RFB_E_INVALID, "state_in of stream " + std::to_string(s) + " holds an id that is not a state of this NFA");
+        }
     cudaSetDevice(ctx->device);
     (void)cudaGetLastError();
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;

@@ -48,6 +48,7 @@ struct OutDev {
 
 struct NfaDev {
     uint32_t n_states;
+    uint32_t n_ref_states;       // states of the NFA as loaded (ids in state_in / state_out rows, indices of id_of_orig / sub_of_ref)
     const uint32_t *row_ptr;     // [n_states + 1]
     const uint32_t *trans;       // [nnz]  {symbol[31:24], target[23:0]}  Design/FPGA.v:888-898
     // edge-grouped CSR (general kernel)

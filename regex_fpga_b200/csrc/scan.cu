@@ -111,7 +111,8 @@ __device__ __noinline__ bool ring_contains(uint32_t lb, uint32_t from, uint32_t 
 __device__ __noinline__ void lane_export_state(const uint32_t *orig_of_id, const uint32_t *mem_ptr, const uint16_t *mem_ids,
                                                unsigned int *dst, uint32_t cap, bool append, uint64_t P0, uint64_t P1, uint32_t lb,
                                                uint32_t from, uint32_t to, uint32_t row, uint32_t rmask, uint32_t d) {
-    uint32_t n = append ? dst[0] : 0u;                 // an earlier part's overflow mark (0xFFFFFFFF) stays an overflow
+    uint32_t n = append ? dst[0] : 0u;
+    if (n == 0xFFFFFFFFu) return;                      // an earlier part's overflow mark stays
     for (int w = 0; w < 2; w++) {
         uint64_t bits = w ? P1 : P0;
         while (bits) {
@@ -235,9 +236,10 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                 P0 = 0; P1 = 0; rp = 0; re = 0; wp = 0; filt = 0; d = 0; k = 0;
                 if (batch.state_in) {   // resume: the stream's active set as left by an earlier call
                     const unsigned int *stt = batch.state_in + (size_t)sid * (1u + batch.state_cap);
-                    const uint32_t ns = min(stt[0], batch.state_cap);
+                    const uint32_t ns = stt[0] <= batch.state_cap ? stt[0] : 0u;   // an overflow mark cannot be resumed: treated as empty (rfb_scan rejects it)
                     bool fits = true;
                     for (uint32_t q = 0; q < ns; q++) {
+                        if (stt[1 + q] >= nfa.n_ref_states) continue;                // not a state: ignored
                         const uint32_t id = nfa.id_of_orig[stt[1 + q]];
                         if (id == 0xFFFFFFFFu) continue;          // a state of another part
                         if (id < nsb) { if (W == 1 || id < 64) P0 |= 1ull << (id & 63); else P1 |= 1ull << (id & 63); }
@@ -459,12 +461,13 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
         bool dense = false;
         if (batch.state_in) {   // resume from the set an earlier call left
             const unsigned int *stt = batch.state_in + (size_t)sid * (1u + batch.state_cap);
-            const uint32_t ns = min(stt[0], batch.state_cap);
+            const uint32_t ns = stt[0] <= batch.state_cap ? stt[0] : 0u;
             ncur = 0;
             for (uint32_t base = 0; base < ns; base += 32) {             // keep the members that belong to this (sub-)NFA
                 const uint32_t i = base + lane;
                 uint32_t s = i < ns ? stt[1 + i] : 0xFFFFFFFFu;
-                if (i < ns && nfa.sub_of_ref) s = nfa.sub_of_ref[s];
+                if (s >= nfa.n_ref_states) s = 0xFFFFFFFFu;               // not a state: ignored
+                else if (nfa.sub_of_ref) s = nfa.sub_of_ref[s];
                 const uint32_t m = __ballot_sync(0xffffffffu, s != 0xFFFFFFFFu);
                 if (s != 0xFFFFFFFFu) list_cur[ncur + __popc(m & ((1u << lane) - 1u))] = s;
                 ncur += __popc(m);

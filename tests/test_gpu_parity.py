@@ -360,6 +360,39 @@ def test_resume_when_the_ring_overflows_in_the_last_step(gpu_ctx, seed):
     assert sorted(recs_tuple(a.records) + recs_tuple(b.records)) == recs_tuple(want["recs"])
 
 
+def test_state_rows_that_cannot_be_resumed(gpu_ctx, snort):
+    """An overflow mark or a foreign id in state_in: rfb_scan refuses host rows; the device-pointer variant ignores
+    such entries instead of indexing out of bounds.  A cut NFA whose set outgrows state_cap says so in every part."""
+    import torch
+    nfa = gpu_ctx.nfa_from_entries(snort.entries)
+    data = WL.make_batch_numpy("whi", snort.lo, snort.hi, 4, 200, 256, seed=3)
+    st = np.zeros((4, 8), np.uint32)
+    st[:, 0] = 1
+    st[2, 0] = R.STATE_OVERFLOW
+    with pytest.raises(R.RfbError, match="overflow mark"):
+        nfa.scan(data, 4, n_steps=200, stride=256, state_in=st)
+    st[2, 0] = 1
+    st[1, 1] = snort.n_states + 5
+    with pytest.raises(R.RfbError, match="not a state"):
+        nfa.scan(data, 4, n_steps=200, stride=256, state_in=st)
+    # device rows are not readable by the host: bad entries are skipped (stream 1 resumes from the empty set)
+    st[1, 1] = 0xFFFFFF00
+    st[3, 0] = R.STATE_OVERFLOW
+    d_st = torch.from_numpy(st.view(np.int32)).to("cuda:0")
+    d_data = torch.from_numpy(data).to("cuda:0")
+    counts = torch.zeros(snort.n_states, dtype=torch.int64, device="cuda:0")
+    for flags in (0, R.SCAN_FORCE_WARP):
+        r = nfa.scan_device(d_data.data_ptr(), d_data.numel(), 4, 200, 256, counts.data_ptr(), None, 0, flags=flags,
+                            cuda_stream=torch.cuda.current_stream().cuda_stream, state_in_ptr=d_st.data_ptr(), state_cap=7)
+        assert r.n_symbols == 800
+    # 3 replicas behind one start state: every replica's ".*" state is active after one symbol, 3+ ids > state_cap 2
+    E, n = WL.replicate_nfa(snort.entries, snort.n_states, 3)
+    big = gpu_ctx.nfa_from_entries(E, n)
+    assert big.info["n_parts"] >= 2
+    a = big.scan(data, 4, n_steps=50, stride=256, want_state=True, state_cap=2)
+    assert np.all(a.state[:, 0] == R.STATE_OVERFLOW)
+
+
 def test_config5_replicated_large_nfa_adversarial(gpu_ctx, snort):
     """BASELINE config 5: 7 x snort_16 behind one start state (66 592 states, beyond the FPGA's own 16-bit
     rd_address) with adversarial high-activity streams and hi-trace windows.  The tables of the whole NFA do not fit
