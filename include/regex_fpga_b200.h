@@ -197,6 +197,17 @@ int rfb_scan_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *batch, ui
 /* Completes an RFB_SCAN_ASYNC call: synchronises and fills the scalar outputs of *result. */
 int rfb_scan_collect(rfb_ctx *ctx, rfb_result *result);
 
+/* Pipelined host path: rfb_scan with up to TWO host batches in flight, so that the next batch's H2D copy
+ * overlaps the tail of the current scan, its record sort and the D2H of its results (a lone rfb_scan
+ * leaves the PCIe link idle during those).  rfb_scan_submit enqueues the copy and the kernels of a
+ * uniformly strided batch (no offsets / steps / state_in / state_out: RFB_E_UNSUPPORTED) and returns;
+ * the batch data, result->counts and result->records must stay valid (and should be pinned) until
+ * rfb_scan_wait has returned that result.  rfb_scan_wait completes the OLDEST submitted batch, fills
+ * its rfb_result exactly as rfb_scan would, and stores its address in *done (nullable). */
+int rfb_scan_submit(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *batch, uint32_t flags,
+                    rfb_result *result);
+int rfb_scan_wait(rfb_ctx *ctx, rfb_result **done);
+
 /* Informational: the testbench's "Total no. cycles" (testbench_BLK_Mem.sv:52,84) for an M-entry
  * (lo,hi) trace pair, from the closed-form cycle model of Design/FPGA.v, evaluated on
  * the GPU from the per-step active sets of both streams.  Host pointers. */

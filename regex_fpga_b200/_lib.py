@@ -59,6 +59,8 @@ SIGNATURES = {
     "rfb_scan": (C.c_int, [_VP, _VP, C.POINTER(rfb_batch), C.c_uint32, C.POINTER(rfb_result)]),
     "rfb_scan_device": (C.c_int, [_VP, _VP, C.POINTER(rfb_batch), C.c_uint32, _VP, C.POINTER(rfb_result)]),
     "rfb_scan_collect": (C.c_int, [_VP, C.POINTER(rfb_result)]),
+    "rfb_scan_submit": (C.c_int, [_VP, _VP, C.POINTER(rfb_batch), C.c_uint32, C.POINTER(rfb_result)]),
+    "rfb_scan_wait": (C.c_int, [_VP, C.POINTER(C.POINTER(rfb_result))]),
     "rfb_fpga_cycles": (C.c_int, [_VP, _VP, _U8P, _U8P, C.c_uint32, C.POINTER(C.c_uint64)]),
 }
 

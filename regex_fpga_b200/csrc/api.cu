@@ -34,6 +34,21 @@ struct rfb_ctx {
     uint32_t *d_sort_hist = nullptr; size_t d_sort_hist_cap = 0;
     unsigned int *d_state_in = nullptr; size_t d_state_in_cap = 0;     // resumable scans: per-stream sets in / out
     unsigned int *d_state_out = nullptr; size_t d_state_out_cap = 0;
+    // pipelined host path (rfb_scan_submit / rfb_scan_wait): two batches in flight, each with its own buffers
+    struct Slot {
+        uint8_t *d_data = nullptr; size_t d_data_cap = 0;
+        ScanGlobals *g = nullptr, *g_host = nullptr;
+        unsigned long long *d_counts = nullptr; size_t d_counts_cap = 0;
+        rfb_match *d_records = nullptr; size_t d_records_cap = 0;
+        uint2 *rescan = nullptr; size_t rescan_cap = 0;
+        cudaEvent_t ev_reset = nullptr, ev0 = nullptr, ev1 = nullptr;
+        bool busy = false;
+        // what rfb_scan_wait needs
+        const rfb_nfa *nfa = nullptr; rfb_batch batch{}; uint32_t flags = 0; rfb_result *res = nullptr;
+        uint32_t launches = 0; bool want_counts = false;
+    } slot[2];
+    int slot_head = 0, slots_busy = 0;     // oldest busy slot, number in flight
+    cudaStream_t post_stream = nullptr;    // sort + D2H of a finished batch beside the next batch's kernel
     // state of the last enqueued scan (for rfb_scan_collect)
     cudaStream_t last_stream = nullptr;
     unsigned long long last_symbols = 0;
@@ -184,6 +199,14 @@ void rfb_ctx_destroy(rfb_ctx *ctx) {
     cudaFree(ctx->d_data); cudaFree(ctx->d_offsets); cudaFree(ctx->d_steps);
     cudaFree(ctx->d_counts); cudaFree(ctx->d_records); cudaFree(ctx->d_state_in); cudaFree(ctx->d_state_out);
     cudaFree(ctx->d_sort_tmp); cudaFree(ctx->d_sort_hist);
+    if (ctx->post_stream) { cudaStreamSynchronize(ctx->post_stream); cudaStreamDestroy(ctx->post_stream); }
+    for (auto &s : ctx->slot) {
+        cudaFree(s.d_data); cudaFree(s.g); cudaFree(s.d_counts); cudaFree(s.d_records); cudaFree(s.rescan);
+        if (s.g_host) cudaFreeHost(s.g_host);
+        if (s.ev_reset) cudaEventDestroy(s.ev_reset);
+        if (s.ev0) cudaEventDestroy(s.ev0);
+        if (s.ev1) cudaEventDestroy(s.ev1);
+    }
     delete ctx;
 }
 
@@ -516,17 +539,20 @@ int rfb_scan_collect(rfb_ctx *ctx, rfb_result *res) {
 
 // Enqueues the scan kernels of one batch (device pointers) on `st`.  The globals must already be reset.
 static int enqueue_kernels(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flags, const rfb_result *res,
-                           cudaStream_t st, uint32_t *launches, unsigned int chunk_streams = 0) {
+                           cudaStream_t st, uint32_t *launches, unsigned int chunk_streams = 0,
+                           ScanGlobals *g = nullptr, uint2 *rescan = nullptr) {
+    if (!g) g = ctx->g;
+    if (!rescan) rescan = ctx->rescan;
     BatchDev bd;
     bd.data = b->data; bd.n_streams = b->n_streams; bd.stride = b->stride;
     bd.offsets = reinterpret_cast<const unsigned long long *>(b->offsets);
     bd.steps = b->steps; bd.n_steps = b->n_steps; bd.stream_id_base = b->stream_id_base;
-    bd.chunk_streams = chunk_streams; bd.ready = &ctx->g->chunks_ready;
+    bd.chunk_streams = chunk_streams; bd.ready = &g->chunks_ready;
     bd.pos_base = b->pos_base; bd.state_cap = b->state_cap; bd.state_in = b->state_in; bd.state_out = b->state_out;
     OutDev od;
     od.counts = (flags & RFB_SCAN_NO_COUNTS) ? nullptr : reinterpret_cast<unsigned long long *>(res->counts);
     od.records = res->records; od.capacity = res->records ? res->record_capacity : 0;
-    od.g = ctx->g; od.rescan = ctx->rescan;
+    od.g = g; od.rescan = rescan;
     // a row no kernel writes must read as "overflow", never as stale memory
     if (b->state_out && b->n_streams)
         CU(ctx, cudaMemsetAsync(b->state_out, 0xFF, (size_t)b->n_streams * (1 + (size_t)b->state_cap) * 4, st));
@@ -534,7 +560,7 @@ static int enqueue_kernels(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b,
         bool first = true;
         for (const Part &p : nfa->parts) {   // one pass over the batch per part; reports of different parts are disjoint
             if (!first) {
-                CU(ctx, cudaMemsetAsync(&ctx->g->next_stream, 0, 3 * sizeof(unsigned int), st));
+                CU(ctx, cudaMemsetAsync(&g->next_stream, 0, 3 * sizeof(unsigned int), st));
                 bd.chunk_streams = 0;        // the batch is resident once the first pass has consumed it
             }
             bd.count_symbols = first ? 1u : 0u;
@@ -699,6 +725,120 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     res->n_matches = dr.n_matches; res->n_records = dr.n_records; res->n_dropped = dr.n_dropped;
     res->n_symbols = dr.n_symbols; res->n_rescanned = dr.n_rescanned; res->gpu_ms = dr.gpu_ms;
     res->n_launches = dr.n_launches;
+    return RFB_OK;
+}
+
+// ---- pipelined host path ------------------------------------------------------------------------------
+// rfb_scan spends its last milliseconds on the tail of the kernel, the record sort and the D2H of the results while
+// the PCIe link idles.  With two batches in flight the next batch's H2D copy runs during all of that: the copy stream
+// resets the slot's globals and streams the chunks, the compute stream runs the kernels (stream order keeps batches
+// apart), and rfb_scan_wait finishes the oldest batch on a third stream.
+static int slot_setup(rfb_ctx *ctx, rfb_ctx::Slot &s) {
+    if (s.g) return RFB_OK;
+    CU(ctx, cudaMalloc(reinterpret_cast<void **>(&s.g), sizeof(ScanGlobals)));
+    CU(ctx, cudaMallocHost(reinterpret_cast<void **>(&s.g_host), sizeof(ScanGlobals)));
+    CU(ctx, cudaEventCreateWithFlags(&s.ev_reset, cudaEventDisableTiming));
+    CU(ctx, cudaEventCreate(&s.ev0));
+    CU(ctx, cudaEventCreate(&s.ev1));
+    if (!ctx->post_stream) CU(ctx, cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking));
+    return RFB_OK;
+}
+
+int rfb_scan_submit(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flags, rfb_result *res) {
+    if (!ctx || !nfa || !res) return fail(ctx, RFB_E_INVALID, "NULL argument");
+    if (nfa->ctx != ctx) return fail(ctx, RFB_E_INVALID, "nfa belongs to another context");
+    int rc = check_batch(ctx, b, true);
+    if (rc) return rc;
+    if (b->offsets || b->steps || b->state_in || b->state_out)
+        return fail(ctx, RFB_E_UNSUPPORTED, "rfb_scan_submit takes uniformly strided batches without per-stream lengths or resumed state");
+    if (ctx->slots_busy == 2) return fail(ctx, RFB_E_INVALID, "two batches are in flight: call rfb_scan_wait first");
+    cudaSetDevice(ctx->device);
+    (void)cudaGetLastError();
+    rfb_ctx::Slot &s = ctx->slot[(ctx->slot_head + ctx->slots_busy) & 1];
+    rc = slot_setup(ctx, s);
+    if (rc) return rc;
+    cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
+    const size_t padded = ((size_t)b->data_bytes + 15) / 16 * 16 + 16;
+    CU(ctx, ensure(s.d_data, s.d_data_cap, padded));
+    if (s.rescan_cap < b->n_streams) CU(ctx, ensure(s.rescan, s.rescan_cap, (size_t)b->n_streams));
+    rfb_batch db = *b;
+    db.data = s.d_data;
+    rfb_result dr = *res;
+    s.want_counts = res->counts && !(flags & RFB_SCAN_NO_COUNTS);
+    if (s.want_counts) {
+        CU(ctx, ensure(s.d_counts, s.d_counts_cap, (size_t)nfa->host.n_states));
+        dr.counts = reinterpret_cast<uint64_t *>(s.d_counts);
+        CU(ctx, cudaMemsetAsync(s.d_counts, 0, (size_t)nfa->host.n_states * 8, cs));
+    } else dr.counts = nullptr;
+    if (res->records && res->record_capacity) {
+        CU(ctx, ensure(s.d_records, s.d_records_cap, (size_t)res->record_capacity));
+        dr.records = s.d_records;
+    } else { dr.records = nullptr; dr.record_capacity = 0; }
+    const uint32_t kflags = flags & (RFB_SCAN_FORCE_WARP | RFB_SCAN_NO_COUNTS);
+    // the copy stream owns the slot's globals until the kernel starts: it must not queue behind the previous
+    // batch's kernel, or the copy could not overlap it
+    CU(ctx, cudaMemsetAsync(s.g, 0, sizeof(ScanGlobals), cs));
+    CU(ctx, cudaEventRecord(s.ev_reset, cs));
+    const bool lane_path = nfa->parts[0].img.ok && !(flags & RFB_SCAN_FORCE_WARP);
+    uint64_t n_chunks = 1;
+    if (lane_path && b->n_streams >= 64 && b->stride > 0) n_chunks = std::min<uint64_t>(16, std::max<uint64_t>(1, b->data_bytes / (64ull << 20)));
+    const uint64_t chunk_streams = n_chunks > 1 ? ((b->n_streams + n_chunks - 1) / n_chunks + 31) / 32 * 32 : 0;
+    uint32_t launches = 0;
+    if (n_chunks > 1) {
+        for (uint64_t c = 0; c < n_chunks; c++) {
+            const uint64_t s0 = std::min<uint64_t>(c * chunk_streams, b->n_streams);
+            const uint64_t s1 = std::min<uint64_t>((c + 1) * chunk_streams, b->n_streams);
+            const size_t lo = (size_t)(s0 * b->stride);
+            const size_t hi = (c + 1 == n_chunks || s1 == b->n_streams) ? (size_t)b->data_bytes : (size_t)(s1 * b->stride);
+            if (hi > lo) CU(ctx, cudaMemcpyAsync(s.d_data + lo, b->data + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+            CU(ctx, cudaMemcpyAsync(&s.g->chunks_ready, &ctx->chunk_vals[c], sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
+        }
+        CU(ctx, cudaStreamWaitEvent(st, s.ev_reset, 0));
+        CU(ctx, cudaEventRecord(s.ev0, st));
+        rc = enqueue_kernels(ctx, nfa, &db, kflags, &dr, st, &launches, (unsigned int)chunk_streams, s.g, s.rescan);
+        if (rc) return rc;
+    } else {
+        if (b->data_bytes) CU(ctx, cudaMemcpyAsync(s.d_data, b->data, b->data_bytes, cudaMemcpyHostToDevice, cs));
+        CU(ctx, cudaEventRecord(s.ev_reset, cs));
+        CU(ctx, cudaStreamWaitEvent(st, s.ev_reset, 0));
+        CU(ctx, cudaEventRecord(s.ev0, st));
+        rc = enqueue_kernels(ctx, nfa, &db, kflags, &dr, st, &launches, 0, s.g, s.rescan);
+        if (rc) return rc;
+    }
+    CU(ctx, cudaEventRecord(s.ev1, st));
+    s.nfa = nfa; s.batch = *b; s.flags = flags; s.res = res; s.launches = launches; s.busy = true;
+    ctx->slots_busy++;
+    return RFB_OK;
+}
+
+int rfb_scan_wait(rfb_ctx *ctx, rfb_result **done) {
+    if (!ctx) return fail(ctx, RFB_E_INVALID, "NULL argument");
+    if (done) *done = nullptr;
+    if (ctx->slots_busy == 0) return fail(ctx, RFB_E_INVALID, "no batch is in flight");
+    cudaSetDevice(ctx->device);
+    rfb_ctx::Slot &s = ctx->slot[ctx->slot_head];
+    cudaStream_t ps = ctx->post_stream;
+    rfb_result *res = s.res;
+    // whatever happens below, the slot is released
+    s.busy = false; ctx->slot_head ^= 1; ctx->slots_busy--;
+    CU(ctx, cudaStreamWaitEvent(ps, s.ev1, 0));
+    CU(ctx, cudaMemcpyAsync(s.g_host, s.g, sizeof(ScanGlobals), cudaMemcpyDeviceToHost, ps));
+    CU(ctx, cudaStreamSynchronize(ps));
+    const ScanGlobals &g = *s.g_host;
+    const uint64_t n_records = res->records ? std::min<uint64_t>(g.n_matches, res->record_capacity) : 0;
+    if ((s.flags & RFB_SCAN_SORT_RECORDS) && n_records > 1) {
+        const int rc = sort_on_device(ctx, s.nfa, &s.batch, true, s.d_records, n_records, ps);
+        if (rc) return rc;
+    }
+    if (s.want_counts) CU(ctx, cudaMemcpyAsync(res->counts, s.d_counts, (size_t)s.nfa->host.n_states * 8, cudaMemcpyDeviceToHost, ps));
+    if (n_records) CU(ctx, cudaMemcpyAsync(res->records, s.d_records, n_records * sizeof(rfb_match), cudaMemcpyDeviceToHost, ps));
+    CU(ctx, cudaStreamSynchronize(ps));
+    float ms = 0.f;
+    CU(ctx, cudaEventElapsedTime(&ms, s.ev0, s.ev1));
+    res->n_matches = g.n_matches; res->n_records = n_records; res->n_dropped = g.n_matches - n_records;
+    res->n_symbols = s.batch.n_streams * (unsigned long long)s.batch.n_steps;
+    res->n_rescanned = g.n_rescan_total; res->gpu_ms = ms; res->n_launches = s.launches;
+    if (done) *done = res;
     return RFB_OK;
 }
 

@@ -27,16 +27,18 @@ __global__ void __launch_bounds__(256) sort_hist_kernel(const rfb_match *in, uns
     hist[(size_t)threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];     // digit-major: scan order = output order
 }
 
-// exclusive prefix sum over hist[256 * n_blocks] (one CTA; n_blocks is a few hundred)
-__global__ void __launch_bounds__(1024) sort_scan_kernel(uint32_t *hist, uint32_t total) {
-    __shared__ uint32_t part[1024];
-    const uint32_t per = (total + 1023) / 1024;
+// exclusive prefix sum over hist[256 * n_blocks] (one CTA; n_blocks is a few hundred).  256 threads at <= 32
+// registers: small enough to run on an SM that a lane-kernel CTA occupies (pipelined host path, api.cu)
+constexpr int SCAN_THREADS = 256;
+__global__ void __launch_bounds__(SCAN_THREADS) sort_scan_kernel(uint32_t *hist, uint32_t total) {
+    __shared__ uint32_t part[SCAN_THREADS];
+    const uint32_t per = (total + SCAN_THREADS - 1) / SCAN_THREADS;
     const uint32_t lo = threadIdx.x * per, hi = lo + per < total ? lo + per : total;
     uint32_t s = 0;
     for (uint32_t i = lo; i < hi; i++) s += hist[i];
     part[threadIdx.x] = s;
     __syncthreads();
-    if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < 1024; i++) { const uint32_t v = part[i]; part[i] = run; run += v; } }
+    if (threadIdx.x == 0) { uint32_t run = 0; for (int i = 0; i < SCAN_THREADS; i++) { const uint32_t v = part[i]; part[i] = run; run += v; } }
     __syncthreads();
     uint32_t run = part[threadIdx.x];
     for (uint32_t i = lo; i < hi; i++) { const uint32_t v = hist[i]; hist[i] = run; run += v; }
@@ -76,7 +78,7 @@ cudaError_t launch_sort_records(rfb_match *records, rfb_match *tmp, unsigned lon
     for (int byte = 0; byte < 12; byte++) {
         if (!((key_bytes >> byte) & 1u)) continue;
         sort_hist_kernel<<<n_blocks, 256, 0, stream>>>(src, n, byte, hist, n_blocks);
-        sort_scan_kernel<<<1, 1024, 0, stream>>>(hist, 256u * n_blocks);
+        sort_scan_kernel<<<1, SCAN_THREADS, 0, stream>>>(hist, 256u * n_blocks);
         sort_scatter_kernel<<<n_blocks, 32, 0, stream>>>(src, dst, n, byte, hist, n_blocks);
         rfb_match *t = src; src = dst; dst = t;
     }

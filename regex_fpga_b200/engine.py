@@ -114,6 +114,7 @@ class Context:
         self._h = h
         self.device_id = device_id
         self._nfas = weakref.WeakSet()
+        self._inflight = []          # (result, arrays...) of submitted batches, oldest first
 
     def close(self):
         if getattr(self, "_h", None):
@@ -262,6 +263,38 @@ class Nfa:
         r.record_capacity = record_capacity
         _check(self._L.rfb_scan(self.ctx._h, self._h, C.byref(b), flags, C.byref(r)), self.ctx._h)
         return ScanResult(counts, records[: r.n_records], r, state_out)
+
+    # -- pipelined host path: two batches in flight (rfb_scan_submit / rfb_scan_wait) --
+    def submit(self, data, n_streams, n_steps, stride, records_out, counts_out=None, flags=SCAN_SORT_RECORDS,
+               stream_id_base=0, pos_base=0):
+        """Enqueue the copy and the scan of a uniformly strided host batch and return at once; `wait()` completes
+        the oldest submitted batch.  data / records_out / counts_out must stay alive (and should be pinned) until
+        then; at most two batches may be in flight."""
+        data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        assert records_out.dtype == MATCH_DTYPE and records_out.flags.c_contiguous
+        b = rfb_batch()
+        b.data = data.ctypes.data if data.size else None
+        b.data_bytes = data.size
+        b.n_streams = n_streams
+        b.stride = stride
+        b.n_steps = n_steps
+        b.stream_id_base = stream_id_base
+        b.pos_base = pos_base
+        r = rfb_result()
+        if counts_out is not None:
+            assert counts_out.dtype == np.uint64 and counts_out.size >= self.n_states and counts_out.flags.c_contiguous
+            r.counts = counts_out.ctypes.data
+        r.records = records_out.ctypes.data if records_out.size else None
+        r.record_capacity = records_out.size
+        _check(self._L.rfb_scan_submit(self.ctx._h, self._h, C.byref(b), flags, C.byref(r)), self.ctx._h)
+        self.ctx._inflight.append((r, data, records_out, counts_out))
+
+    def wait(self):
+        """Complete the oldest submitted batch: ScanResult over the arrays given to submit()."""
+        done = C.POINTER(rfb_result)()
+        _check(self._L.rfb_scan_wait(self.ctx._h, C.byref(done)), self.ctx._h)
+        r, _data, records, counts = self.ctx._inflight.pop(0)
+        return ScanResult(counts, records[: r.n_records], r, None)
 
     # -- device pointers in, device results out (for benchmarks: no PCIe in the timed region) --
     def scan_device(self, data_ptr, data_bytes, n_streams, n_steps, stride, counts_ptr=None, records_ptr=None,

@@ -477,6 +477,40 @@ def test_host_path_chunked_overlap_matches_device_path(gpu_ctx, snort):
     assert ragged.n_symbols == int(steps.sum())
 
 
+def test_pipelined_host_path_matches_rfb_scan(gpu_ctx, snort):
+    """rfb_scan_submit / rfb_scan_wait: two host batches in flight (the second batch's H2D copy overlaps the first
+    one's tail, sort and D2H).  Results must equal rfb_scan's, batch by batch, in submission order; a third submit
+    without a wait, a wait with nothing in flight and ragged batches are refused."""
+    import torch
+    nfa = gpu_ctx.nfa_from_entries(snort.entries)
+    n = 100000                                                        # 154 MB: chunked copy + gated kernel
+    batches = [WL.make_batch_torch("wmix", snort.lo, snort.hi, n, "cuda:0", 1500, 1536, seed=0x5EED0100 + i).cpu().pin_memory()
+               for i in range(3)]
+    cap = 1 << 19
+    want = [nfa.scan(b.numpy(), n, n_steps=1500, stride=1536, record_capacity=cap, stream_id_base=10 * i) for i, b in enumerate(batches)]
+    recs = [torch.empty(cap * 12, dtype=torch.uint8, pin_memory=True).numpy().view(R.engine.MATCH_DTYPE) for _ in range(2)]
+    cnts = [torch.empty(snort.n_states, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64) for _ in range(2)]
+    got = []
+    for i, b in enumerate(batches):
+        nfa.submit(b.numpy(), n, 1500, 1536, recs[i & 1], cnts[i & 1], stream_id_base=10 * i)
+        if i >= 1:
+            r = nfa.wait()
+            got.append((recs_tuple(r.records), r.counts.copy(), r.n_matches, r.n_symbols))
+    r = nfa.wait()
+    got.append((recs_tuple(r.records), r.counts.copy(), r.n_matches, r.n_symbols))
+    for w, (g_recs, g_counts, g_m, g_sym) in zip(want, got):
+        assert g_m == w.n_matches and g_sym == n * 1500 and np.array_equal(g_counts, w.counts) and g_recs == recs_tuple(w.records)
+    with pytest.raises(R.RfbError, match="no batch"):
+        nfa.wait()
+    small = batches[0].numpy()[:64]
+    nfa.submit(small, 64, 1500, 1536, recs[0], cnts[0])
+    nfa.submit(small, 64, 1500, 1536, recs[1], cnts[1])
+    with pytest.raises(R.RfbError, match="two batches"):
+        nfa.submit(small, 64, 1500, 1536, recs[0], cnts[0])
+    a, b2 = nfa.wait(), nfa.wait()
+    assert a.n_matches == b2.n_matches and recs_tuple(a.records) == recs_tuple(b2.records)
+
+
 def test_device_side_record_sort(gpu_ctx, snort):
     """RFB_SCAN_SORT_RECORDS on the device path: a stable LSD radix sort over the 12-byte records must give exactly
     the canonical (stream, pos, state) order, also with a large stream_id_base / pos_base (all key bytes in use)."""

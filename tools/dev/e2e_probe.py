@@ -28,5 +28,18 @@ with R.Context(0) as ctx:
         os.environ["RFB_CHUNKS"] = str(ch); os.environ["RFB_CHUNK_MB"] = str(mb)
         run(f"sorted, pinned, chunks={ch}", records_out=prec, counts_out=pcnt, flags=1)
     del os.environ["RFB_CHUNKS"], os.environ["RFB_CHUNK_MB"]
+    # pipelined: two batches in flight
+    prec2 = torch.empty(cap * 12, dtype=torch.uint8, pin_memory=True).numpy().view(MATCH_DTYPE)
+    pcnt2 = torch.empty(nfa.n_states, dtype=torch.int64, pin_memory=True).numpy().view(np.uint64)
+    bufs = [(prec, pcnt), (prec2, pcnt2)]
+    for flags in (1, 0):
+        K = 6
+        t0 = time.perf_counter()
+        for i in range(K):
+            nfa.submit(hn, n, 1500, 1536, bufs[i & 1][0], bufs[i & 1][1], flags=flags)
+            if i: out = nfa.wait()
+        out = nfa.wait()
+        dt = (time.perf_counter() - t0) / K
+        print(f"pipelined (flags={flags})                    wall {dt*1e3:7.2f} ms per batch  = {n*1500*8/dt/1e9:6.1f} Gbit/s  gpu_ms {out.gpu_ms:7.2f} recs {out.n_records}", flush=True)
     run("no records, pinned counts", record_capacity=0, counts_out=pcnt, flags=0)
     run("no records, no counts", record_capacity=0, want_counts=False, flags=4)
