@@ -27,7 +27,7 @@ with R.Context(0) as ctx:
         (E, n), syms = random_nfa(rng, n_states=int(rng.integers(3, 300)), alphabet=int(rng.integers(2, 16)),
                                   p_sticky=float(rng.choice([0.0, 0.1, 0.3])), max_fanout=int(rng.integers(1, 4)),
                                   unanchored=bool(rng.integers(0, 2)))
-        big = i % 5 == 4 and n >= 40
+        big = i % 5 == 4 and n >= 40 and not os.environ.get("STRESS_NO_BIG")
         if big:   # enough replicas that the tables no longer fit one SM: the NFA is cut into parts
             copies = int(np.ceil(40000 / (n - 1)))
             try:
