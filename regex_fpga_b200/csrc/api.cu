@@ -614,6 +614,33 @@ int rfb_scan_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
     return rc;
 }
 
+// Host path: uniformly strided batches on the lane kernel are copied in up to 16 chunks of whole streams; after each
+// chunk the copy stream bumps *ready (a counter in the scan's globals) and the kernel's warps wait for the chunk of the
+// stream they take.  Returns the chunk size in streams (0: one copy, no gating).
+static uint64_t plan_chunks(const rfb_nfa *nfa, const rfb_batch *b, uint32_t flags, uint64_t *n_chunks_out) {
+    const bool lane_path = nfa->parts[0].img.ok && !(flags & RFB_SCAN_FORCE_WARP);
+    uint64_t n_chunks = 1;
+    if (lane_path && !b->offsets && b->n_streams >= 64 && b->stride > 0) {
+        uint64_t max_chunks = 16, min_bytes = 64ull << 20;
+        if (const char *e = getenv("RFB_CHUNKS")) max_chunks = std::min<uint64_t>(MAX_CHUNKS, std::max(1, atoi(e)));
+        if (const char *e = getenv("RFB_CHUNK_MB")) min_bytes = (uint64_t)std::max(1, atoi(e)) << 20;
+        n_chunks = std::min<uint64_t>(max_chunks, std::max<uint64_t>(1, b->data_bytes / min_bytes));
+    }
+    *n_chunks_out = n_chunks;
+    return n_chunks > 1 ? ((b->n_streams + n_chunks - 1) / n_chunks + 31) / 32 * 32 : 0;
+}
+static int copy_chunks(rfb_ctx *ctx, const rfb_batch *b, uint8_t *d_data, unsigned int *ready, uint64_t n_chunks, uint64_t chunk_streams, cudaStream_t cs) {
+    for (uint64_t c = 0; c < n_chunks; c++) {
+        const uint64_t s0 = std::min<uint64_t>(c * chunk_streams, b->n_streams);
+        const uint64_t s1 = std::min<uint64_t>((c + 1) * chunk_streams, b->n_streams);
+        const size_t lo = (size_t)(s0 * b->stride);
+        const size_t hi = (c + 1 == n_chunks || s1 == b->n_streams) ? (size_t)b->data_bytes : (size_t)(s1 * b->stride);
+        if (hi > lo) CU(ctx, cudaMemcpyAsync(d_data + lo, b->data + lo, hi - lo, cudaMemcpyHostToDevice, cs));
+        CU(ctx, cudaMemcpyAsync(ready, &ctx->chunk_vals[c], sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
+    }
+    return RFB_OK;
+}
+
 int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flags, rfb_result *res) {
     if (!ctx || !nfa || !res) return fail(ctx, RFB_E_INVALID, "NULL argument");
     if (nfa->ctx != ctx) return fail(ctx, RFB_E_INVALID, "nfa belongs to another context");
@@ -669,35 +696,19 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     const uint32_t kflags = flags & (RFB_SCAN_FORCE_WARP | RFB_SCAN_NO_COUNTS);
     CU(ctx, cudaMemsetAsync(ctx->g, 0, sizeof(ScanGlobals), st));
 
-    // Uniformly strided batches are copied in up to 16 chunks of whole streams on the copy stream; after each
-    // chunk the copy stream bumps g->chunks_ready.  ONE lane-kernel launch over the whole batch runs beside the
-    // copies: its warps take streams in ascending order and wait for their chunk's counter, so the kernel
-    // overlaps the H2D transfer at full occupancy.  Other batches (explicit offsets, general kernel only) wait
-    // for the whole copy.
+    // ONE lane-kernel launch over the whole batch runs beside the chunked copy (plan_chunks / copy_chunks above): its
+    // warps take streams in ascending order and wait for their chunk's counter, so the kernel overlaps the H2D transfer
+    // at full occupancy.  Other batches (explicit offsets, general kernel only) wait for the whole copy.
     uint32_t launches = 0;
-    const bool lane_path = nfa->parts[0].img.ok && !(flags & RFB_SCAN_FORCE_WARP);
     uint64_t n_chunks = 1;
-    if (lane_path && !b->offsets && b->n_streams >= 64 && b->stride > 0)
-    {
-        uint64_t max_chunks = 16, min_bytes = 64ull << 20;
-        if (const char *e = getenv("RFB_CHUNKS")) max_chunks = std::min<uint64_t>(MAX_CHUNKS, std::max(1, atoi(e)));
-        if (const char *e = getenv("RFB_CHUNK_MB")) min_bytes = (uint64_t)std::max(1, atoi(e)) << 20;
-        n_chunks = std::min<uint64_t>(max_chunks, std::max<uint64_t>(1, b->data_bytes / min_bytes));
-    }
-    const uint64_t chunk_streams = n_chunks > 1 ? ((b->n_streams + n_chunks - 1) / n_chunks + 31) / 32 * 32 : 0;
+    const uint64_t chunk_streams = plan_chunks(nfa, b, flags, &n_chunks);
     CU(ctx, cudaEventRecord(ctx->ev_chunk[0], st));                  // globals reset before the first flag write
     CU(ctx, cudaStreamWaitEvent(cs, ctx->ev_chunk[0], 0));
     CU(ctx, cudaEventRecord(ctx->ev0, st));
     if (n_chunks > 1) {
         // copies first: with pageable host memory they complete before the launch below (no overlap, no hazard)
-        for (uint64_t c = 0; c < n_chunks; c++) {
-            const uint64_t s0 = std::min<uint64_t>(c * chunk_streams, b->n_streams);
-            const uint64_t s1 = std::min<uint64_t>((c + 1) * chunk_streams, b->n_streams);
-            const size_t lo = (size_t)(s0 * b->stride);
-            const size_t hi = (c + 1 == n_chunks || s1 == b->n_streams) ? (size_t)b->data_bytes : (size_t)(s1 * b->stride);
-            if (hi > lo) CU(ctx, cudaMemcpyAsync(ctx->d_data + lo, b->data + lo, hi - lo, cudaMemcpyHostToDevice, cs));
-            CU(ctx, cudaMemcpyAsync(&ctx->g->chunks_ready, &ctx->chunk_vals[c], sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
-        }
+        rc = copy_chunks(ctx, b, ctx->d_data, &ctx->g->chunks_ready, n_chunks, chunk_streams, cs);
+        if (rc) return rc;
         rc = enqueue_kernels(ctx, nfa, &db, kflags, &dr, st, &launches, (unsigned int)chunk_streams);
         if (rc) return rc;
     } else {
@@ -779,20 +790,12 @@ int rfb_scan_submit(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
     // batch's kernel, or the copy could not overlap it
     CU(ctx, cudaMemsetAsync(s.g, 0, sizeof(ScanGlobals), cs));
     CU(ctx, cudaEventRecord(s.ev_reset, cs));
-    const bool lane_path = nfa->parts[0].img.ok && !(flags & RFB_SCAN_FORCE_WARP);
     uint64_t n_chunks = 1;
-    if (lane_path && b->n_streams >= 64 && b->stride > 0) n_chunks = std::min<uint64_t>(16, std::max<uint64_t>(1, b->data_bytes / (64ull << 20)));
-    const uint64_t chunk_streams = n_chunks > 1 ? ((b->n_streams + n_chunks - 1) / n_chunks + 31) / 32 * 32 : 0;
+    const uint64_t chunk_streams = plan_chunks(nfa, b, flags, &n_chunks);
     uint32_t launches = 0;
     if (n_chunks > 1) {
-        for (uint64_t c = 0; c < n_chunks; c++) {
-            const uint64_t s0 = std::min<uint64_t>(c * chunk_streams, b->n_streams);
-            const uint64_t s1 = std::min<uint64_t>((c + 1) * chunk_streams, b->n_streams);
-            const size_t lo = (size_t)(s0 * b->stride);
-            const size_t hi = (c + 1 == n_chunks || s1 == b->n_streams) ? (size_t)b->data_bytes : (size_t)(s1 * b->stride);
-            if (hi > lo) CU(ctx, cudaMemcpyAsync(s.d_data + lo, b->data + lo, hi - lo, cudaMemcpyHostToDevice, cs));
-            CU(ctx, cudaMemcpyAsync(&s.g->chunks_ready, &ctx->chunk_vals[c], sizeof(unsigned int), cudaMemcpyHostToDevice, cs));
-        }
+        rc = copy_chunks(ctx, b, s.d_data, &s.g->chunks_ready, n_chunks, chunk_streams, cs);
+        if (rc) return rc;
         CU(ctx, cudaStreamWaitEvent(st, s.ev_reset, 0));
         CU(ctx, cudaEventRecord(s.ev0, st));
         rc = enqueue_kernels(ctx, nfa, &db, kflags, &dr, st, &launches, (unsigned int)chunk_streams, s.g, s.rescan);
