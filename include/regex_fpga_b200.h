@@ -22,7 +22,8 @@
 extern "C" {
 #endif
 
-#define RFB_ABI_VERSION 2
+/* 3: + rfb_nfa_describe, execution-image files, rfb_scan_submit / rfb_scan_wait (structs unchanged since 2) */
+#define RFB_ABI_VERSION 3
 
 typedef enum rfb_status {
     RFB_OK = 0,
