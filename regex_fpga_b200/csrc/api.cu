@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -131,6 +132,7 @@ static ImageOptions default_image_options() {
     if (const char *s = std::getenv("RFB_STICKY_WORDS")) opt.sticky_words = std::atoi(s);
     if (const char *s = std::getenv("RFB_BUCKET_BITS")) opt.bucket_bits = std::atoi(s);
     if (const char *s = std::getenv("RFB_STICKY_MIN_SELF")) opt.sticky_min_self = std::atoi(s);
+    if (const char *s = std::getenv("RFB_DFA_ABSORB")) opt.dfa_absorb = std::atoi(s);
     if (const char *s = std::getenv("RFB_DFA_STATES")) { const int v = std::atoi(s); if (v <= 0) opt.accel = 0; else opt.dfa_max_states = (uint32_t)v; }
     // the per-stream rings (16 entries x 1024 streams x 2 bytes) share the SM's shared memory with the tables
     opt.max_bytes = (uint32_t)(MAX_DYN_SMEM - 16 * LANE_THREADS * 2 - 64);
@@ -269,6 +271,32 @@ static int upload_part(rfb_ctx *ctx, Part &p, uint32_t n_states_full, std::strin
     return RFB_OK;
 }
 
+// Building a plan (bucket hash search, start-DFA construction with its greedy move of sticky states, equivalence proof)
+// takes seconds for a large ruleset; a process that loads the same NFA again -- another context, another GPU, a test
+// suite -- gets the plan from a small cache keyed by the image and the options.
+static int plan_build_cached(const uint32_t *entries, size_t n_entries, int64_t n_states, const ImageOptions &opt, bool split,
+                             Plan &plan, std::string &err) {
+    struct Entry { std::vector<uint32_t> entries; int64_t n_states; std::vector<uint64_t> key; Plan plan; };
+    static std::mutex mu;
+    static std::vector<Entry> cache;
+    const std::vector<uint64_t> key = {(uint64_t)opt.sticky_words, (uint64_t)opt.sticky_min_self, (uint64_t)(int64_t)opt.bucket_bits, (uint64_t)opt.accel,
+                                       opt.dfa_max_states, (uint64_t)opt.dfa_absorb, opt.max_bytes, (uint64_t)split};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (const Entry &e : cache)
+            if (e.n_states == n_states && e.key == key && e.entries.size() == n_entries && std::memcmp(e.entries.data(), entries, n_entries * 4) == 0) {
+                plan = e.plan;
+                return RFB_OK;
+            }
+    }
+    const int rc = plan_build(entries, n_entries, n_states, opt, split, plan, err);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() >= 4) cache.erase(cache.begin());
+    cache.push_back(Entry{std::vector<uint32_t>(entries, entries + n_entries), n_states, key, plan});
+    return RFB_OK;
+}
+
 // Uploads a scan plan (imagefile.cpp) to the context's GPU.
 static int nfa_from_plan(rfb_ctx *ctx, Plan &plan, rfb_nfa **out) {
     rfb_nfa *nfa = new (std::nothrow) rfb_nfa();
@@ -310,7 +338,7 @@ int rfb_nfa_from_entries(rfb_ctx *ctx, const uint32_t *entries, size_t n_entries
     *out = nullptr;
     Plan plan;
     std::string err;
-    const int rc = plan_build(entries, n_entries, n_states, default_image_options(), !std::getenv("RFB_NO_SPLIT"), plan, err);
+    const int rc = plan_build_cached(entries, n_entries, n_states, default_image_options(), !std::getenv("RFB_NO_SPLIT"), plan, err);
     if (rc) return fail(ctx, rc, err);
     return nfa_from_plan(ctx, plan, out);
 }
@@ -398,10 +426,10 @@ int rfb_nfa_describe(const rfb_nfa *nfa, char *buf, size_t cap) {
         if (p.img.ok)
             std::snprintf(line, sizeof line,
                           "part %zu: states %u kernel lane image_bytes %u slots %u bucket_bits %u sticky %u sticky_dropped %u "
-                          "dfa %u dfa_states %u dfa_classes %u dfa_beyond_budget %u dfa_list_entries %zu\n",
+                          "dfa %u dfa_states %u dfa_classes %u dfa_beyond_budget %u dfa_list_entries %zu dfa_absorbed_sticky %u\n",
                           g, p.sub.n_states, p.img.h.blob_bytes, p.img.h.n_slots, p.img.h.bucket_bits, p.img.n_sticky,
                           p.img.n_sticky_dropped, p.img.h.accel, p.img.dfa.n, p.img.dfa.ncls, p.img.dfa.n_frontier,
-                          p.img.dfa.act.size());
+                          p.img.dfa.act.size(), p.img.n_absorbed);
         else
             std::snprintf(line, sizeof line, "part %zu: states %u kernel general (%s)\n", g, p.sub.n_states, p.img.why_not.c_str());
         s += line;

@@ -66,7 +66,12 @@ struct ImageOptions {
     int sticky_min_self = 16;   // a state is mask-resident if it self-loops on >= this many symbols
     int bucket_bits = -1;       // -1 = auto; buckets per branching state = 1 << bucket_bits
     int accel = 1;              // build the start DFA for the always-active sticky state
-    uint32_t dfa_max_states = 16384;   // <= 32766 (15-bit ids)
+    uint32_t dfa_max_states = 32766;   // <= 32766 (15-bit ids)
+    int dfa_absorb = 12;        // up to this many sticky states that the start DFA enters are tracked BY the DFA (as ordinary
+                                // members with a self loop) instead of by the mask, while the DFA stays complete: see image_build
+    std::vector<uint32_t> not_sticky;   // internal (image_build): states kept out of the sticky mask
+    bool verify = true;         // internal: trial builds skip the equivalence proof, the final build runs it
+    uint32_t fixed_hash_mul = 0, fixed_hash_shift = 0;   // internal: reuse a bucket hash instead of searching (mul != 0)
     uint32_t max_bytes = 200 * 1024;
 };
 
@@ -99,6 +104,7 @@ struct Image {
     std::vector<uint32_t> orig_of_id;  // internal id -> original state id (0xFFFFFFFF: not a state)
     std::vector<uint32_t> id_of_orig;  // original state id -> internal id
     uint32_t n_sticky = 0;
+    uint32_t n_absorbed = 0;                            // sticky states tracked by the start DFA instead of the mask
     uint32_t n_sticky_dropped = 0;                      // self-looping states that did not fit the mask (run as ordinary states)
     // start DFA (see image.cpp): the successors of the always-active state A (bit 0) that are neither sticky nor
     // accepting are never materialised; a per-stream DFA state d stands for the set of them that is active.

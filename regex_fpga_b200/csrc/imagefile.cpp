@@ -26,6 +26,7 @@
 #include "../../include/regex_fpga_b200.h"
 #include <cstdio>
 #include <cstring>
+#include <map>
 
 namespace rfb {
 namespace {
@@ -136,17 +137,29 @@ int plan_build(const uint32_t *entries, size_t n_entries, int64_t n_states, cons
     // Prefer the coarsest cut whose parts all get full-quality tables (>= 8 buckets per branching state, every
     // self-looping state in the mask): such a part runs at the speed of a small NFA, and a part that misses
     // either costs far more than one extra pass over the batch.  Otherwise the coarsest cut that fits at all.
+    // The cuts are explored with plain images (no sticky states moved into the start DFA: that search is the slow part
+    // of a build and does not change whether a part fits); the parts of the chosen cut are then built in full, once
+    // per distinct sub-NFA (the replicas of config 5 are identical).
+    ImageOptions fast = opt;
+    fast.dfa_absorb = 0;
     std::vector<PlanPart> fallback;
     for (uint32_t limit = 24000; limit >= 1500; limit /= 2) {
         std::vector<std::vector<uint32_t>> groups;
         nfa_components(plan.host, limit, groups);
         if (groups.empty()) break;
         std::vector<PlanPart> parts(groups.size());
+        std::map<std::vector<uint32_t>, size_t> first_with;     // sub-NFA image -> first part that has it
         bool all_ok = true, all_good = true;
         for (size_t g = 0; g < groups.size(); g++) {
             rc = nfa_extract(plan.host, groups[g], parts[g].sub, parts[g].to_orig, err);
-            if (rc == RFB_OK) rc = image_build(parts[g].sub, opt, parts[g].img, err);
             if (rc) return rc;
+            auto it = first_with.find(parts[g].sub.entries);
+            if (it != first_with.end()) parts[g].img = parts[it->second].img;
+            else {
+                rc = image_build(parts[g].sub, fast, parts[g].img, err);
+                if (rc) return rc;
+                first_with.emplace(parts[g].sub.entries, g);
+            }
             all_ok = all_ok && parts[g].img.ok;
             all_good = all_good && parts[g].img.ok && parts[g].img.h.bucket_bits >= 3 && parts[g].img.n_sticky_dropped == 0;
         }
@@ -154,6 +167,19 @@ int plan_build(const uint32_t *entries, size_t n_entries, int64_t n_states, cons
         if (all_ok && fallback.empty()) fallback.swap(parts);
     }
     if (!fallback.empty()) plan.parts.swap(fallback);
+    if (plan.parts.size() > 1 && opt.dfa_absorb > 0) {
+        std::map<std::vector<uint32_t>, size_t> first_with;
+        for (size_t g = 0; g < plan.parts.size(); g++) {
+            PlanPart &p = plan.parts[g];
+            if (!p.img.ok) continue;
+            auto it = first_with.find(p.sub.entries);
+            if (it != first_with.end()) { p.img = plan.parts[it->second].img; continue; }
+            Image full;
+            std::string e2;
+            if (image_build(p.sub, opt, full, e2) == RFB_OK && full.ok) p.img = std::move(full);
+            first_with.emplace(p.sub.entries, g);
+        }
+    }
     return RFB_OK;
 }
 

@@ -581,6 +581,9 @@ def test_large_batch_properties(gpu_ctx, snort):
 
 
 def test_describe_reports_the_start_dfa(gpu_ctx, snort, l7, monkeypatch):
+    text = gpu_ctx.nfa_from_entries(snort.entries).describe()       # sticky states moved into a still complete DFA
+    assert "kernel lane" in text and "dfa_beyond_budget 0 " in text and "dfa_absorbed_sticky 0" not in text
+    monkeypatch.setenv("RFB_DFA_ABSORB", "0")
     for rs, states in ((snort, 8495), (l7, 1763)):
         text = gpu_ctx.nfa_from_entries(rs.entries).describe()
         assert "kernel lane" in text and f"dfa_states {states} " in text and "dfa_beyond_budget 0 " in text   # complete DFAs

@@ -17,10 +17,14 @@ def test_shipped_rulesets_verify(snort, l7, sticky_words, bucket_bits):
         assert info["n_slots"] <= 0x8000
 
 
-def test_shipped_ruleset_shapes(snort, l7):
+def test_shipped_ruleset_shapes(snort, l7, monkeypatch):
     s = R.image_check(snort.entries)
     assert (s["n_states"], s["n_transitions"], s["n_accepting"]) == (9514, 79856, 536)
+    assert 50 <= s["n_sticky"] < 65 and s["sticky_words"] == 1   # some of the 67 moved into the start DFA: one mask word is enough
+    monkeypatch.setenv("RFB_DFA_ABSORB", "0")
+    s = R.image_check(snort.entries)
     assert s["n_sticky"] >= 65          # 23 full + 42 all-but-newline self-loop states
+    monkeypatch.delenv("RFB_DFA_ABSORB")
     f = R.image_check(l7.entries)
     assert (f["n_states"], f["n_transitions"], f["n_accepting"]) == (2794, 124977, 204)
 

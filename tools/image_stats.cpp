@@ -26,7 +26,7 @@ int main(int argc, char **argv) {
     std::vector<uint32_t> E; std::vector<uint8_t> lo, hi; std::string err;
     if (coe_parse_file(argv[1], E, err) || mem_parse_file(argv[2], lo, err) || mem_parse_file(argv[3], hi, err)) { fprintf(stderr, "%s\n", err.c_str()); return 1; }
     int n_streams = argc > 4 ? atoi(argv[4]) : 1024;
-    ImageOptions opt; if (argc > 5) opt.bucket_bits = atoi(argv[5]); if (argc > 6) opt.sticky_words = atoi(argv[6]); if (argc > 7) opt.dfa_max_states = atoi(argv[7]);
+    ImageOptions opt; if (argc > 5) opt.bucket_bits = atoi(argv[5]); if (argc > 6) opt.sticky_words = atoi(argv[6]); if (argc > 7) opt.dfa_max_states = atoi(argv[7]); if (argc > 8) opt.dfa_absorb = atoi(argv[8]);
     Nfa nfa; Image img;
     if (nfa_from_entries(E.data(), E.size(), -1, nfa, err) || image_build(nfa, opt, img, err) || !img.ok) { fprintf(stderr, "image: %s %s\n", err.c_str(), img.why_not.c_str()); return 1; }
     const ImageHeader &h = img.h;
@@ -34,7 +34,7 @@ int main(int argc, char **argv) {
     const uint32_t *memb = (const uint32_t *)&img.blob[h.off_memb];
     const uint32_t *sdesc = (const uint32_t *)&img.blob[h.off_sdesc];
     const uint32_t W = h.sticky_words, ms = 32 * W, L = 1500;
-    printf("start DFA: %u states (%u beyond the budget), %u classes, %zu insertion-list entries\n", img.dfa.n, img.dfa.n_frontier, img.dfa.ncls, img.dfa.act.size());
+    printf("start DFA: %u states (%u beyond the budget), %u classes, %zu insertion-list entries, %u sticky states absorbed\n", img.dfa.n, img.dfa.n_frontier, img.dfa.ncls, img.dfa.act.size(), img.n_absorbed);
     printf("image: slots %u gbase %u nsb %u W %u bucket_bits %u bytes %u sets %u sticky %u hash mul %u sh %u\n", h.n_slots, h.gbase, h.nsb, W, h.bucket_bits, h.blob_bytes, h.n_sets, img.n_sticky, h.hash_mul, h.hash_shift);
     Stats st[2];
     std::vector<uint64_t> dhist;
