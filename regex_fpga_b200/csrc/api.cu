@@ -442,20 +442,16 @@ int rfb_nfa_describe(const rfb_nfa *nfa, char *buf, size_t cap) {
 int rfb_image_check(const uint32_t *entries, size_t n_entries, int64_t n_states, int sticky_words, int bucket_bits,
                     rfb_nfa_info *info) {
     if (!entries || !info) return fail(nullptr, RFB_E_INVALID, "NULL argument");
-    Nfa host;
-    Image img;
-    Ecsr ecsr;
     std::string err;
-    int rc = nfa_from_entries(entries, n_entries, n_states, host, err);
-    if (rc) return fail(nullptr, rc, err);
     ImageOptions opt = default_image_options();
     if (sticky_words > 0) opt.sticky_words = sticky_words;
     if (bucket_bits > 0) opt.bucket_bits = bucket_bits;
     else if (!std::getenv("RFB_BUCKET_BITS")) opt.bucket_bits = -1;
-    rc = image_build(host, opt, img, err);
+    Plan plan;
+    const int rc = plan_build_cached(entries, n_entries, n_states, opt, false, plan, err);
     if (rc) return fail(nullptr, rc, err);
-    fill_info(host, img, info);
-    if (!img.ok) g_err = img.why_not;
+    fill_info(plan.host, plan.parts[0].img, info);
+    if (!plan.parts[0].img.ok) g_err = plan.parts[0].img.why_not;
     return RFB_OK;
 }
 

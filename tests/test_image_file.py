@@ -45,7 +45,8 @@ def test_multi_part_plan_round_trip(snort, tmp_path):
     assert info["n_parts"] >= 2 and info["image_ok"] == 1 and info["n_states"] == n3
 
 
-def test_corruption_is_refused(snort, tmp_path):
+def test_corruption_is_refused(l7, tmp_path):
+    snort = l7                                                          # the smaller ruleset: every accepted or refused mutant costs a full proof
     p = tmp_path / "s.rfbimg"
     R.image_file_build(snort.entries, p)
     raw = bytearray(p.read_bytes())
