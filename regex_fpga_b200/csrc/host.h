@@ -3,6 +3,7 @@
 #include <cstddef>
 #include <cstdint>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace rfb {
@@ -72,6 +73,7 @@ struct ImageOptions {
     std::vector<uint32_t> not_sticky;   // internal (image_build): states kept out of the sticky mask
     bool verify = true;         // internal: trial builds skip the equivalence proof, the final build runs it
     uint32_t fixed_hash_mul = 0, fixed_hash_shift = 0;   // internal: reuse a bucket hash instead of searching (mul != 0)
+    bool probe_dfa_only = false;   // internal: stop after the start DFA (its size decides whether a sticky state may move into it)
     uint32_t max_bytes = 200 * 1024;
 };
 
@@ -118,6 +120,7 @@ struct Image {
         std::vector<uint16_t> mem_ids;     // ... as internal ids (never sticky, never accepting)
         uint32_t n_frontier = 0;           // states whose rows fall back to a shorter history
     } dfa;
+    std::vector<std::pair<int, uint32_t>> dfa_sticky_targets;   // sticky states the DFA enters: (-symbols they fire on, original id)
 };
 
 // tab entry encoding

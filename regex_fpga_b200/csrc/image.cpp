@@ -154,6 +154,137 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
         if (sticky_bit[s] < 0 && !is_accept(s) && !is_single(s)) { img.id_of_orig[s] = next_id; next_id += NB; branchers.push_back(s); }
     const uint32_t srow_base = next_id;   // sticky rows are sized once the hash is known
 
+    // ---- start DFA --------------------------------------------------------------------------------------
+    std::vector<uint32_t> cmap(256, 0);                       // per symbol: DFA class | h(c) << 16
+    Image::Dfa &D = img.dfa;
+    D = Image::Dfa();
+    D.dt.assign(1, 0); D.dta.assign(1, 0); D.mem_ptr.assign(2, 0);
+    if (accel) {
+        auto ordinary = [&](uint32_t s) { return sticky_bit[s] < 0 && !is_accept(s); };
+        // states the DFA can hold: reachable from A through ordinary states
+        std::vector<char> in_r(N, 0);
+        std::vector<uint32_t> stack;
+        for (const Edge &e : a_edges) if (ordinary(e.tgt) && !in_r[e.tgt]) { in_r[e.tgt] = 1; stack.push_back(e.tgt); }
+        while (!stack.empty()) {
+            const uint32_t s = stack.back(); stack.pop_back();
+            for (const Edge &e : edges[s]) if (ordinary(e.tgt) && !in_r[e.tgt]) { in_r[e.tgt] = 1; stack.push_back(e.tgt); }
+        }
+        // symbol classes: two symbols are equivalent iff no edge of A or of those states tells them apart
+        std::vector<uint32_t> cls(256, 0);
+        uint32_t ncls = 1;
+        {
+            std::map<SymSet, int> distinct;
+            for (const Edge &e : a_edges) distinct.emplace(e.syms, 0);
+            for (uint32_t s = 0; s < N; s++) if (in_r[s]) for (const Edge &e : edges[s]) distinct.emplace(e.syms, 0);
+            for (const auto &kv : distinct) {
+                std::map<std::pair<uint32_t, bool>, uint32_t> split;
+                for (uint32_t c = 0; c < 256; c++) {
+                    auto it = split.emplace(std::make_pair(cls[c], kv.first.has(c)), (uint32_t)split.size()).first;
+                    cls[c] = it->second;
+                }
+                ncls = (uint32_t)split.size();
+            }
+        }
+        std::vector<uint32_t> rep(ncls, 0xFFFFFFFFu);
+        for (uint32_t c = 0; c < 256; c++) if (rep[cls[c]] == 0xFFFFFFFFu) rep[cls[c]] = c;
+        for (uint32_t c = 0; c < 256; c++) cmap[c] = cls[c];
+
+        // successors per (state the DFA can hold, class) and of A per class: the expansion below only concatenates
+        std::vector<int32_t> r_index(N, -1);
+        uint32_t n_r = 0;
+        for (uint32_t s = 0; s < N; s++) if (in_r[s]) r_index[s] = (int32_t)n_r++;
+        std::vector<std::vector<uint32_t>> succ_cls((size_t)n_r * ncls), a_cls(ncls);
+        for (uint32_t q = 0; q < ncls; q++) for (const Edge &e : a_edges) if (e.syms.has(rep[q])) a_cls[q].push_back(e.tgt);
+        for (uint32_t s = 0; s < N; s++) if (in_r[s])
+            for (const Edge &e : edges[s]) for (uint32_t q = 0; q < ncls; q++) if (e.syms.has(rep[q])) succ_cls[(size_t)r_index[s] * ncls + q].push_back(e.tgt);
+
+        std::vector<char> entered_sticky(N, 0);               // sticky states that appear in an insertion list
+        const size_t ACT_CAP = 6u << 20;                      // insertion-list entries (12 MB)
+        uint32_t budget = std::min<uint32_t>(std::max<uint32_t>(opt.dfa_max_states, ncls + 2), 32766);
+        for (;; budget = std::max<uint32_t>(ncls + 2, budget / 2)) {
+            // breadth-first subset construction; states keyed by their ordinary members (original ids, sorted)
+            std::map<std::vector<uint32_t>, uint32_t> id_of;
+            std::vector<std::vector<uint32_t>> members(2);
+            std::vector<uint32_t> fail(2, 1);
+            std::map<std::vector<uint16_t>, uint32_t> act_of;
+            id_of[{}] = 1;
+            D.dt.assign((size_t)2 * ncls, 0); D.dta.assign((size_t)2 * ncls, 0);
+            D.act.assign(1, 0);                                // index 0: unused
+            D.n_frontier = 0;
+            bool act_overflow = false;
+            uint64_t work = 0;                                 // edge-list visits so far: bounds the load time on NFAs whose subsets explode
+            const uint64_t WORK_CAP = 60ull * 1000 * 1000;
+            std::vector<uint32_t> T, ord;
+            std::vector<uint16_t> lst;
+            bool probe_abort = false;                          // probe: the first subset beyond the budget settles the answer
+            for (uint32_t d = 1; d < members.size() && !act_overflow && !probe_abort; d++) {
+                if (D.dt.size() < (size_t)(d + 1) * ncls) { D.dt.resize((size_t)(d + 1) * ncls, 0); D.dta.resize((size_t)(d + 1) * ncls, 0); }
+                bool fell_back = false;
+                work += (uint64_t)ncls * (members[d].size() + 1);
+                for (uint32_t q = 0; q < ncls; q++) {
+                    T = a_cls[q];
+                    for (uint32_t m : members[d]) { const auto &v = succ_cls[(size_t)r_index[m] * ncls + q]; T.insert(T.end(), v.begin(), v.end()); }
+                    std::sort(T.begin(), T.end());
+                    T.erase(std::unique(T.begin(), T.end()), T.end());
+                    ord.clear(); lst.clear();
+                    for (uint32_t t : T) {
+                        if (ordinary(t)) ord.push_back(t);
+                        else { lst.push_back((uint16_t)img.id_of_orig[t]); if (sticky_bit[t] > 0) entered_sticky[t] = 1; }
+                    }
+                    uint32_t nd;
+                    auto it = id_of.find(ord);
+                    if (it != id_of.end()) nd = it->second;
+                    else if (members.size() < budget && work < WORK_CAP) {
+                        nd = (uint32_t)members.size();
+                        id_of.emplace(ord, nd);
+                        members.push_back(ord);
+                        fail.push_back(d == 1 ? 1u : (uint32_t)(D.dt[(size_t)fail[d] * ncls + q] & 0x7FFFu));
+                    } else {
+                        // beyond the budget: continue from the longest tracked suffix history (its state holds a
+                        // subset of ord) and insert the rest explicitly
+                        fell_back = true;
+                        if (opt.probe_dfa_only) { probe_abort = true; break; }
+                        nd = d == 1 ? 1u : (uint32_t)(D.dt[(size_t)fail[d] * ncls + q] & 0x7FFFu);
+                        if (!std::includes(ord.begin(), ord.end(), members[nd].begin(), members[nd].end())) nd = 1;
+                        for (uint32_t t : ord) if (!std::binary_search(members[nd].begin(), members[nd].end(), t)) lst.push_back((uint16_t)img.id_of_orig[t]);
+                    }
+                    uint32_t at = 0;
+                    if (!lst.empty()) {
+                        std::sort(lst.begin(), lst.end());
+                        auto jt = act_of.find(lst);
+                        if (jt != act_of.end()) at = jt->second;
+                        else {
+                            at = (uint32_t)D.act.size();
+                            act_of.emplace(lst, at);
+                            for (size_t k = 0; k < lst.size(); k++) D.act.push_back((uint16_t)(lst[k] | (k + 1 < lst.size() ? 0x8000u : 0u)));
+                            if (D.act.size() > ACT_CAP) act_overflow = true;
+                        }
+                    }
+                    D.dt[(size_t)d * ncls + q] = (uint16_t)(nd | (at ? 0x8000u : 0u));
+                    D.dta[(size_t)d * ncls + q] = at;
+                }
+                D.n_frontier += fell_back;
+            }
+            if (act_overflow && budget > ncls + 2) continue;
+            if (act_overflow) { img.why_not = "start DFA insertion lists too large"; }
+            D.ncls = ncls; D.n = (uint32_t)members.size();
+            D.mem_ptr.assign(1, 0); D.mem_ids.clear();
+            for (const auto &m : members) {
+                for (uint32_t t : m) D.mem_ids.push_back((uint16_t)img.id_of_orig[t]);
+                D.mem_ptr.push_back((uint32_t)D.mem_ids.size());
+            }
+            break;
+        }
+        for (uint32_t t = 0; t < N; t++) if (entered_sticky[t]) {
+            SymSet fire;
+            for (const Edge &e : edges[t]) for (int w = 0; w < 4; w++) fire.w[w] |= e.syms.w[w];
+            img.dfa_sticky_targets.emplace_back(-fire.count(), t);
+        }
+        std::sort(img.dfa_sticky_targets.begin(), img.dfa_sticky_targets.end());
+    }
+
+    if (opt.probe_dfa_only) { img.n_absorbed = (uint32_t)opt.not_sticky.size(); img.h.accel = accel ? 1u : 0u; img.ok = img.why_not.empty(); return RFB_OK; }
+
     // ---- bucket hash: pick (mul, shift) minimising the expected table lookups per visit -------------
     // A visit with symbol c costs 1 lookup when bucket(c) holds <= 1 edge, 1 + n when it holds n >= 2
     // (indirection + chain).  Symbols that appear on some edge of the state are what the traffic that
@@ -282,123 +413,6 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
         }
     }
 
-    // ---- start DFA --------------------------------------------------------------------------------------
-    std::vector<uint32_t> cmap(256, 0);                       // per symbol: DFA class | h(c) << 16
-    Image::Dfa &D = img.dfa;
-    D = Image::Dfa();
-    D.dt.assign(1, 0); D.dta.assign(1, 0); D.mem_ptr.assign(2, 0);
-    if (accel) {
-        auto ordinary = [&](uint32_t s) { return sticky_bit[s] < 0 && !is_accept(s); };
-        // states the DFA can hold: reachable from A through ordinary states
-        std::vector<char> in_r(N, 0);
-        std::vector<uint32_t> stack;
-        for (const Edge &e : a_edges) if (ordinary(e.tgt) && !in_r[e.tgt]) { in_r[e.tgt] = 1; stack.push_back(e.tgt); }
-        while (!stack.empty()) {
-            const uint32_t s = stack.back(); stack.pop_back();
-            for (const Edge &e : edges[s]) if (ordinary(e.tgt) && !in_r[e.tgt]) { in_r[e.tgt] = 1; stack.push_back(e.tgt); }
-        }
-        // symbol classes: two symbols are equivalent iff no edge of A or of those states tells them apart
-        std::vector<uint32_t> cls(256, 0);
-        uint32_t ncls = 1;
-        {
-            std::map<SymSet, int> distinct;
-            for (const Edge &e : a_edges) distinct.emplace(e.syms, 0);
-            for (uint32_t s = 0; s < N; s++) if (in_r[s]) for (const Edge &e : edges[s]) distinct.emplace(e.syms, 0);
-            for (const auto &kv : distinct) {
-                std::map<std::pair<uint32_t, bool>, uint32_t> split;
-                for (uint32_t c = 0; c < 256; c++) {
-                    auto it = split.emplace(std::make_pair(cls[c], kv.first.has(c)), (uint32_t)split.size()).first;
-                    cls[c] = it->second;
-                }
-                ncls = (uint32_t)split.size();
-            }
-        }
-        std::vector<uint32_t> rep(ncls, 0xFFFFFFFFu);
-        for (uint32_t c = 0; c < 256; c++) if (rep[cls[c]] == 0xFFFFFFFFu) rep[cls[c]] = c;
-        for (uint32_t c = 0; c < 256; c++) cmap[c] = cls[c];
-
-        // successors per (state the DFA can hold, class) and of A per class: the expansion below only concatenates
-        std::vector<int32_t> r_index(N, -1);
-        uint32_t n_r = 0;
-        for (uint32_t s = 0; s < N; s++) if (in_r[s]) r_index[s] = (int32_t)n_r++;
-        std::vector<std::vector<uint32_t>> succ_cls((size_t)n_r * ncls), a_cls(ncls);
-        for (uint32_t q = 0; q < ncls; q++) for (const Edge &e : a_edges) if (e.syms.has(rep[q])) a_cls[q].push_back(e.tgt);
-        for (uint32_t s = 0; s < N; s++) if (in_r[s])
-            for (const Edge &e : edges[s]) for (uint32_t q = 0; q < ncls; q++) if (e.syms.has(rep[q])) succ_cls[(size_t)r_index[s] * ncls + q].push_back(e.tgt);
-
-        const size_t ACT_CAP = 6u << 20;                      // insertion-list entries (12 MB)
-        uint32_t budget = std::min<uint32_t>(std::max<uint32_t>(opt.dfa_max_states, ncls + 2), 32766);
-        for (;; budget = std::max<uint32_t>(ncls + 2, budget / 2)) {
-            // breadth-first subset construction; states keyed by their ordinary members (original ids, sorted)
-            std::map<std::vector<uint32_t>, uint32_t> id_of;
-            std::vector<std::vector<uint32_t>> members(2);
-            std::vector<uint32_t> fail(2, 1);
-            std::map<std::vector<uint16_t>, uint32_t> act_of;
-            id_of[{}] = 1;
-            D.dt.assign((size_t)2 * ncls, 0); D.dta.assign((size_t)2 * ncls, 0);
-            D.act.assign(1, 0);                                // index 0: unused
-            D.n_frontier = 0;
-            bool act_overflow = false;
-            uint64_t work = 0;                                 // edge-list visits so far: bounds the load time on NFAs whose subsets explode
-            const uint64_t WORK_CAP = 60ull * 1000 * 1000;
-            std::vector<uint32_t> T, ord;
-            std::vector<uint16_t> lst;
-            for (uint32_t d = 1; d < members.size() && !act_overflow; d++) {
-                if (D.dt.size() < (size_t)(d + 1) * ncls) { D.dt.resize((size_t)(d + 1) * ncls, 0); D.dta.resize((size_t)(d + 1) * ncls, 0); }
-                bool fell_back = false;
-                work += (uint64_t)ncls * (members[d].size() + 1);
-                for (uint32_t q = 0; q < ncls; q++) {
-                    T = a_cls[q];
-                    for (uint32_t m : members[d]) { const auto &v = succ_cls[(size_t)r_index[m] * ncls + q]; T.insert(T.end(), v.begin(), v.end()); }
-                    std::sort(T.begin(), T.end());
-                    T.erase(std::unique(T.begin(), T.end()), T.end());
-                    ord.clear(); lst.clear();
-                    for (uint32_t t : T) { if (ordinary(t)) ord.push_back(t); else lst.push_back((uint16_t)img.id_of_orig[t]); }
-                    uint32_t nd;
-                    auto it = id_of.find(ord);
-                    if (it != id_of.end()) nd = it->second;
-                    else if (members.size() < budget && work < WORK_CAP) {
-                        nd = (uint32_t)members.size();
-                        id_of.emplace(ord, nd);
-                        members.push_back(ord);
-                        fail.push_back(d == 1 ? 1u : (uint32_t)(D.dt[(size_t)fail[d] * ncls + q] & 0x7FFFu));
-                    } else {
-                        // beyond the budget: continue from the longest tracked suffix history (its state holds a
-                        // subset of ord) and insert the rest explicitly
-                        fell_back = true;
-                        nd = d == 1 ? 1u : (uint32_t)(D.dt[(size_t)fail[d] * ncls + q] & 0x7FFFu);
-                        if (!std::includes(ord.begin(), ord.end(), members[nd].begin(), members[nd].end())) nd = 1;
-                        for (uint32_t t : ord) if (!std::binary_search(members[nd].begin(), members[nd].end(), t)) lst.push_back((uint16_t)img.id_of_orig[t]);
-                    }
-                    uint32_t at = 0;
-                    if (!lst.empty()) {
-                        std::sort(lst.begin(), lst.end());
-                        auto jt = act_of.find(lst);
-                        if (jt != act_of.end()) at = jt->second;
-                        else {
-                            at = (uint32_t)D.act.size();
-                            act_of.emplace(lst, at);
-                            for (size_t k = 0; k < lst.size(); k++) D.act.push_back((uint16_t)(lst[k] | (k + 1 < lst.size() ? 0x8000u : 0u)));
-                            if (D.act.size() > ACT_CAP) act_overflow = true;
-                        }
-                    }
-                    D.dt[(size_t)d * ncls + q] = (uint16_t)(nd | (at ? 0x8000u : 0u));
-                    D.dta[(size_t)d * ncls + q] = at;
-                }
-                D.n_frontier += fell_back;
-            }
-            if (act_overflow && budget > ncls + 2) continue;
-            if (act_overflow) { img.why_not = "start DFA insertion lists too large"; }
-            D.ncls = ncls; D.n = (uint32_t)members.size();
-            D.mem_ptr.assign(1, 0); D.mem_ids.clear();
-            for (const auto &m : members) {
-                for (uint32_t t : m) D.mem_ids.push_back((uint16_t)img.id_of_orig[t]);
-                D.mem_ptr.push_back((uint32_t)D.mem_ids.size());
-            }
-            break;
-        }
-    }
-
     for (uint32_t c = 0; c < 256; c++) cmap[c] = (cmap[c] & 0xFFFFu) | (hfull(c, best_mul, best_sh) << 16);
 
     // ---- class membership bitmaps ---------------------------------------------------------------------
@@ -488,6 +502,7 @@ int image_build(const Nfa &nfa, const ImageOptions &opt_in, Image &img, std::str
     if (rc != RFB_OK || !img.ok || !img.h.accel || opt.dfa_absorb <= 0 || img.dfa.n_frontier != 0) return rc;
     ImageOptions trial_opt = opt;
     trial_opt.verify = false;
+    trial_opt.probe_dfa_only = true;
     trial_opt.bucket_bits = (int)img.h.bucket_bits;
     trial_opt.fixed_hash_mul = img.h.hash_mul; trial_opt.fixed_hash_shift = img.h.hash_shift;   // the search is the slow part of a build
     std::vector<uint32_t> rejected;
@@ -498,23 +513,9 @@ int image_build(const Nfa &nfa, const ImageOptions &opt_in, Image &img, std::str
     for (bool progress = true; progress && trials < max_trials && kept < opt.dfa_absorb;) {
         progress = false;
         // sticky states the current DFA enters, by the number of symbols on which they fire
-        const ImageHeader &h = best.h;
-        const uint32_t W = h.sticky_words, mstride = 32u * W;
         std::vector<std::pair<int, uint32_t>> cands;
-        std::vector<char> seen(h.nsb, 0);
-        for (uint16_t v : best.dfa.act) {
-            const uint32_t id = v & 0x7FFFu;
-            if (id == 0 || id >= h.nsb || seen[id]) continue;
-            seen[id] = 1;
-            const uint32_t s = best.orig_of_id[id];
-            if (s == 0xFFFFFFFFu || std::find(rejected.begin(), rejected.end(), s) != rejected.end()) continue;
-            int fires = 0;
-            for (uint32_t c = 0; c < 256; c++) {
-                const uint64_t *M = reinterpret_cast<const uint64_t *>(&best.blob[h.off_mask + c * mstride + 16]) + W;
-                fires += (int)((M[id >> 6] >> (id & 63)) & 1);
-            }
-            if (fires >= 4) cands.emplace_back(-fires, s);
-        }
+        for (const auto &cd : best.dfa_sticky_targets)
+            if (-cd.first >= 4 && std::find(rejected.begin(), rejected.end(), cd.second) == rejected.end()) cands.push_back(cd);
         std::sort(cands.begin(), cands.end());
         for (const auto &cd : cands) {
             if (trials >= max_trials || kept >= opt.dfa_absorb) break;
@@ -538,8 +539,8 @@ int image_build(const Nfa &nfa, const ImageOptions &opt_in, Image &img, std::str
         }
     }
     if (!best_verified) {   // the final choice goes through the full proof like any image
-        opt.bucket_bits = (int)best.h.bucket_bits;
-        opt.fixed_hash_mul = best.h.hash_mul; opt.fixed_hash_shift = best.h.hash_shift;
+        opt.bucket_bits = (int)img.h.bucket_bits;
+        opt.fixed_hash_mul = img.h.hash_mul; opt.fixed_hash_shift = img.h.hash_shift;
         Image final_img;
         rc = image_build_one(nfa, opt, final_img, err);
         if (rc != RFB_OK || !final_img.ok) { err.clear(); return RFB_OK; }   // keep the verified baseline in img
