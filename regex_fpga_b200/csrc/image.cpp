@@ -44,6 +44,7 @@
 #include <array>
 #include <cstring>
 #include <map>
+#include <unordered_map>
 
 namespace rfb {
 namespace {
@@ -63,6 +64,14 @@ struct SymSet {
 struct Edge { uint32_t tgt; SymSet syms; };  // tgt = ORIGINAL state id
 
 inline uint32_t align16(uint32_t x) { return (x + 15u) & ~15u; }
+
+struct VecHash {
+    size_t operator()(const std::vector<uint32_t> &v) const {
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (uint32_t x : v) { h ^= x; h *= 0x100000001b3ull; }
+        return (size_t)h;
+    }
+};
 
 int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::string &err) {
     img = Image();
@@ -203,7 +212,8 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
         uint32_t budget = std::min<uint32_t>(std::max<uint32_t>(opt.dfa_max_states, ncls + 2), 32766);
         for (;; budget = std::max<uint32_t>(ncls + 2, budget / 2)) {
             // breadth-first subset construction; states keyed by their ordinary members (original ids, sorted)
-            std::map<std::vector<uint32_t>, uint32_t> id_of;
+            std::unordered_map<std::vector<uint32_t>, uint32_t, VecHash> id_of;
+            id_of.reserve(budget * 2);
             std::vector<std::vector<uint32_t>> members(2);
             std::vector<uint32_t> fail(2, 1);
             std::map<std::vector<uint16_t>, uint32_t> act_of;
