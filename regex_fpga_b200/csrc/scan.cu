@@ -2,8 +2,9 @@
 //
 //  scan_lane_kernel : the hot path.  One THREAD per stream, 1024 threads per SM, the whole execution
 //      image (image.cpp) staged into shared memory with bulk async copies (cp.async.bulk -> UBLKCP),
-//      per-stream state = sticky bit mask in registers + a short ring of transient state ids in
-//      shared memory (column-major, bank-conflict-free).  Every lane walks its own stream at its own
+//      per-stream state = sticky bit mask and start-DFA state in registers (the DFA's tables are in global
+//      memory, L1/L2-resident) + a short ring of transient state ids in shared memory (column-major,
+//      bank-conflict-free).  Every lane walks its own stream at its own
 //      pace (no per-symbol warp synchronisation): the loop is flattened so that one iteration costs
 //      one random shared-memory lookup per lane.  Input bytes arrive as 16-byte ld.global.nc chunks
 //      held in registers.
