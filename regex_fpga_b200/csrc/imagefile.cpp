@@ -18,7 +18,7 @@
 //     u64 n; u8  blob[n]                    mask | cmap | sdesc | tab | memb, staged verbatim into shared memory
 //     u64 n; u32 orig_of_id[n]              internal id -> state id of the part
 //     u64 n; u32 id_of_orig[n]              state id of the part -> internal id
-//     u32 n_sticky; u32 n_sticky_dropped; u32 accel_state
+//     u32 n_sticky; u32 n_sticky_dropped; u32 accel_state; u32 n_absorbed
 //     u32 dfa_ncls; u32 dfa_n; u32 dfa_n_frontier
 //     u64 n; u16 dt[n];  u64 n; u32 dta[n];  u64 n; u16 act[n];  u64 n; u32 mem_ptr[n];  u64 n; u16 mem_ids[n]
 //   u64 fnv1a64 of every byte before it
@@ -197,7 +197,7 @@ int plan_write(const Plan &plan, const std::string &path, std::string &err) {
         if (!p.img.ok) continue;
         w.u32((uint32_t)sizeof(ImageHeader)); w.raw(&p.img.h, sizeof(ImageHeader));
         w.vec(p.img.blob); w.vec(p.img.orig_of_id); w.vec(p.img.id_of_orig);
-        w.u32(p.img.n_sticky); w.u32(p.img.n_sticky_dropped); w.u32(p.img.accel_state);
+        w.u32(p.img.n_sticky); w.u32(p.img.n_sticky_dropped); w.u32(p.img.accel_state); w.u32(p.img.n_absorbed);
         const Image::Dfa &D = p.img.dfa;
         w.u32(D.ncls); w.u32(D.n); w.u32(D.n_frontier);
         w.vec(D.dt); w.vec(D.dta); w.vec(D.act); w.vec(D.mem_ptr); w.vec(D.mem_ids);
@@ -264,7 +264,7 @@ int plan_read(const std::string &path, Plan &plan, std::string &err) {
         if (!ok) { p.img.ok = false; p.img.why_not = "stored without tables"; continue; }
         if (r.u32() != sizeof(ImageHeader) || !r.raw(&p.img.h, sizeof(ImageHeader))) return bad("image header size");
         if (!r.vec(p.img.blob, 1u << 20) || !r.vec(p.img.orig_of_id, 0x8000) || !r.vec(p.img.id_of_orig, 1u << 24)) return bad("truncated");
-        p.img.n_sticky = r.u32(); p.img.n_sticky_dropped = r.u32(); p.img.accel_state = r.u32();
+        p.img.n_sticky = r.u32(); p.img.n_sticky_dropped = r.u32(); p.img.accel_state = r.u32(); p.img.n_absorbed = r.u32();
         Image::Dfa &D = p.img.dfa;
         D.ncls = r.u32(); D.n = r.u32(); D.n_frontier = r.u32();
         if (!r.vec(D.dt, 1u << 24) || !r.vec(D.dta, 1u << 24) || !r.vec(D.act, 1u << 24) || !r.vec(D.mem_ptr, 1u << 16) || !r.vec(D.mem_ids, 1u << 24))
