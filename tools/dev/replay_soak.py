@@ -9,7 +9,7 @@ CSRC=os.path.join(ROOT, 'regex_fpga_b200', 'csrc')
 subprocess.run(['g++','-O2','-std=c++17','-I',CSRC,os.path.join(ROOT, 'tests', 'image_replay.cpp')]+[f'{CSRC}/{f}' for f in ('image.cpp','nfa.cpp','formats.cpp')]+['-o','/tmp/rfb_image_replay'],check=True)
 bad=0; n_abs=0
 for i in range(int(sys.argv[1])):
-    rng=np.random.default_rng(900000+i)
+    rng=np.random.default_rng(900000+int(sys.argv[2] if len(sys.argv)>2 else 0)+i)
     (E,n),syms=random_nfa(rng,n_states=int(rng.integers(5,400)),alphabet=int(rng.integers(2,16)),p_sticky=float(rng.choice([0.05,0.2,0.4])),max_fanout=int(rng.integers(1,4)),unanchored=True)
     L=int(rng.integers(10,200)); ns=int(rng.integers(2,30))
     data=random_streams(rng,syms,ns,L,p_alpha=float(rng.choice([0.7,0.95])))
