@@ -22,8 +22,9 @@
 extern "C" {
 #endif
 
-/* 3: + rfb_nfa_describe, execution-image files, rfb_scan_submit / rfb_scan_wait (structs unchanged since 2) */
-#define RFB_ABI_VERSION 3
+/* 3: + rfb_nfa_describe, execution-image files, rfb_scan_submit / rfb_scan_wait (structs unchanged since 2)
+ * 4: + rfb_nfa_calibrate / rfb_nfa_calibration (structs unchanged) */
+#define RFB_ABI_VERSION 4
 
 typedef enum rfb_status {
     RFB_OK = 0,
@@ -140,6 +141,18 @@ void rfb_nfa_destroy(rfb_nfa *nfa);
 int rfb_nfa_get_info(const rfb_nfa *nfa, rfb_nfa_info *info);
 /* Copies the BRAM image back (n_entries from rfb_nfa_get_info). */
 int rfb_nfa_get_entries(const rfb_nfa *nfa, uint32_t *entries, size_t capacity);
+
+/* Traffic calibration.  The hot kernel keeps the most visited rows of its start-DFA table in shared memory;
+ * which rows those are depends on the traffic.  The library measures it by itself on the first large
+ * (>= 8192 streams) uniformly strided batch an NFA scans -- a host-side walk over 2048 sampled streams, a few
+ * tens of milliseconds, once -- unless RFB_NO_CALIBRATE is set.  rfb_nfa_calibrate does the same explicitly
+ * on a HOST batch of the caller's choice (e.g. before the first timed scan, or again when the traffic has
+ * changed); it waits for scans in flight.  Calibration never changes a result, only speed.  No reference
+ * counterpart: the FPGA reads every row from the same block RAM (Design/FPGA.v:773-795).
+ * rfb_nfa_calibration returns 1 if the NFA is calibrated (0 if not) and reports the sample size in symbols
+ * and the share of the sample's start-DFA lookups that land in shared-memory rows (either may be NULL). */
+int rfb_nfa_calibrate(rfb_ctx *ctx, rfb_nfa *nfa, const rfb_batch *sample);
+int rfb_nfa_calibration(const rfb_nfa *nfa, uint64_t *sample_symbols, double *hot_fraction);
 
 /* ---- host-side format helpers (no GPU involved) --------------------------------------------- */
 /* Replaces: $readmemh of Simulation/input_trace_{hi,lo}_*.mem (testbench_BLK_Mem.sv:34-35).

@@ -72,6 +72,10 @@ int orc_a_run(const uint32_t *E, size_t n_entries, uint32_t size, const uint8_t 
               uint16_t *mc2, uint64_t *cnt1, uint64_t *cnt2, orc_rec *recs, uint64_t cap,
               uint64_t *n_recs, uint64_t *cycles);
 
+/* Oracle A with a per-edge trace of the module's ports (see oracle_a.c), without fast_idle. */
+int orc_a_trace(const uint32_t *E, size_t n_entries, uint32_t size, const uint8_t *lo, const uint8_t *hi,
+                uint64_t M, int addr_bits, uint64_t *trace, uint64_t trace_cap, uint64_t *cycles);
+
 /* Closed-form cycle model, computed from oracle-B sets of both streams. */
 int orc_cycle_model(const uint32_t *E, size_t n_entries, uint32_t size, const uint8_t *lo,
                     const uint8_t *hi, uint64_t M, uint64_t *cycles);

@@ -227,10 +227,10 @@ static uint32_t next_active(const sim_t *s, uint32_t from, uint32_t limit) {
     return limit;
 }
 
-int orc_a_run(const uint32_t *E, size_t n_entries, uint32_t size, const uint8_t *lo,
+static int a_run(const uint32_t *E, size_t n_entries, uint32_t size, const uint8_t *lo,
               const uint8_t *hi, uint64_t M, int addr_bits, int fast_idle, uint16_t *mc1,
               uint16_t *mc2, uint64_t *cnt1, uint64_t *cnt2, orc_rec *recs, uint64_t cap,
-              uint64_t *n_recs, uint64_t *cycles_out) {
+              uint64_t *n_recs, uint64_t *cycles_out, uint64_t *trace, uint64_t trace_cap) {
     if (size == 0 || (size_t)size + 1 > n_entries || addr_bits < 1 || addr_bits > 30) return -1;
     sim_t s;
     memset(&s, 0, sizeof s);
@@ -266,6 +266,9 @@ int orc_a_run(const uint32_t *E, size_t n_entries, uint32_t size, const uint8_t 
         first = 0;
         /* ---- testbench, TB:49-86, evaluated on post-edge values ---- */
         cycles++;                                                     /* TB:52 */
+        if (trace && cycles <= trace_cap)                             /* what the outside sees after this edge */
+            trace[cycles - 1] = (uint64_t)s.r.i | ((uint64_t)s.r.icf << 20) | ((uint64_t)s.r.amf << 21) |
+                                ((uint64_t)s.r.amf2 << 22) | ((uint64_t)s.r.state << 24) | ((uint64_t)s.r.rd_address << 32);
         if (s.r.icf) { ch1 = lo[m]; ch2 = hi[m]; m++; }               /* TB:53-59 */
         if (s.r.amf) {                                                /* TB:61-64 */
             if (mc1) mc1[s.r.i] = (uint16_t)((mc1[s.r.i] + 1u) & 0x3FFu);
@@ -285,6 +288,22 @@ int orc_a_run(const uint32_t *E, size_t n_entries, uint32_t size, const uint8_t 
     if (n_recs) *n_recs = nr;
     if (cycles_out) *cycles_out = cycles;
     return 0;
+}
+
+int orc_a_run(const uint32_t *E, size_t n_entries, uint32_t size, const uint8_t *lo,
+              const uint8_t *hi, uint64_t M, int addr_bits, int fast_idle, uint16_t *mc1,
+              uint16_t *mc2, uint64_t *cnt1, uint64_t *cnt2, orc_rec *recs, uint64_t cap,
+              uint64_t *n_recs, uint64_t *cycles_out) {
+    return a_run(E, n_entries, size, lo, hi, M, addr_bits, fast_idle, mc1, mc2, cnt1, cnt2, recs, cap, n_recs, cycles_out, NULL, 0);
+}
+
+/* Per-edge view of the ports and of `state` (i | input_char_flag << 20 | accepting_match_flag << 21 |
+ * accepting_match_flag_2 << 22 | state << 24 | rd_address << 32, sampled after every posedge, the reset edge
+ * first), for the first trace_cap edges: compared edge by edge with the reference's own Verilog executed through
+ * oracle/vsim (tests/test_ref_vsim.py). */
+int orc_a_trace(const uint32_t *E, size_t n_entries, uint32_t size, const uint8_t *lo, const uint8_t *hi,
+                uint64_t M, int addr_bits, uint64_t *trace, uint64_t trace_cap, uint64_t *cycles_out) {
+    return a_run(E, n_entries, size, lo, hi, M, addr_bits, 0, NULL, NULL, NULL, NULL, NULL, 0, NULL, cycles_out, trace, trace_cap);
 }
 
 /* SURVEY Appendix B.3 closed form, evaluated from functional sets of both streams. */

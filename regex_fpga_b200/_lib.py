@@ -43,6 +43,8 @@ SIGNATURES = {
     "rfb_nfa_destroy": (None, [_VP]),
     "rfb_nfa_get_info": (C.c_int, [_VP, C.POINTER(rfb_nfa_info)]),
     "rfb_nfa_get_entries": (C.c_int, [_VP, _U32P, C.c_size_t]),
+    "rfb_nfa_calibrate": (C.c_int, [_VP, _VP, C.POINTER(rfb_batch)]),
+    "rfb_nfa_calibration": (C.c_int, [_VP, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "rfb_trace_load_mem": (C.c_int, [C.c_char_p, C.POINTER(_U8P), C.POINTER(C.c_size_t)]),
     "rfb_trace_write_mem": (C.c_int, [C.c_char_p, _U8P, C.c_size_t]),
     "rfb_coe_parse": (C.c_int, [C.c_char_p, C.POINTER(_U32P), C.POINTER(C.c_size_t)]),

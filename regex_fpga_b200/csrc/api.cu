@@ -71,6 +71,7 @@ struct Part {
     uint32_t *d_orig = nullptr, *d_map = nullptr, *d_subof = nullptr;
     uint32_t *d_idof = nullptr, *d_dta = nullptr, *d_mem_ptr = nullptr;
     uint16_t *d_dt = nullptr, *d_act = nullptr, *d_mem_ids = nullptr;
+    bool calibrated = false;           // the device copy of the start-DFA tables is ordered by measured visit frequency
     void release() {
         cudaFree(d_entries); cudaFree(d_eptr); cudaFree(d_erec); cudaFree(d_emembs); cudaFree(d_blob);
         cudaFree(d_orig); cudaFree(d_map); cudaFree(d_subof); cudaFree(d_idof); cudaFree(d_dta); cudaFree(d_mem_ptr); cudaFree(d_dt); cudaFree(d_act); cudaFree(d_mem_ids);
@@ -78,6 +79,9 @@ struct Part {
 };
 
 struct rfb_nfa {
+    bool calibrated = false;           // see calibrate_nfa()
+    uint64_t calib_symbols = 0;        // symbols of the sample it was measured on
+    double calib_hot_fraction = 0.0;   // share of the sample's start-DFA lookups that land in rows held in shared memory
     rfb_ctx *ctx = nullptr;
     int device = 0;                    // copy of ctx->device: the context may be destroyed first
     Nfa host;                          // the NFA as loaded
@@ -254,7 +258,9 @@ static int upload_part(rfb_ctx *ctx, Part &p, uint32_t n_states_full, std::strin
         UP(p.d_idof, idof, uint32_t);
         std::vector<uint16_t> mem_ids = im.dfa.mem_ids;
         if (mem_ids.empty()) mem_ids.push_back(0);
-        UP(p.d_dt, im.dfa.dt, uint16_t);
+        std::vector<uint16_t> dt = im.dfa.dt;                          // + 16 bytes: the lane kernel stages whole 16-byte units of the first rows
+        dt.resize(dt.size() + 8, 0);
+        UP(p.d_dt, dt, uint16_t);
         UP(p.d_dta, im.dfa.dta, uint32_t);
         std::vector<uint16_t> act = im.dfa.act;
         if (act.empty()) act.push_back(0);
@@ -506,20 +512,140 @@ int64_t rfb_coe_detect_size(const uint32_t *entries, size_t n_entries) {
 void rfb_free(void *p) { std::free(p); }
 uint32_t rfb_tb_steps(uint32_t trace_entries) { return trace_entries ? trace_entries - 1 : 0; }
 
+static int check_batch(rfb_ctx *ctx, const rfb_batch *b, bool host);
+
+// ---- calibration: start-DFA rows ordered by measured visit frequency ---------------------------------
+// The lane kernel keeps the first rows of the start-DFA table in shared memory (scan.cu: lane_hot_rows); a lookup
+// there costs a bank-conflict-limited gather, a lookup in global memory one L1 wavefront per lane.  Which rows are
+// hot depends on the traffic, not on the NFA alone (breadth-first order or a uniform-byte prior put 68 % of the
+// lookups of the shipped traces into the first 400 rows, the measured order 92 %), so the library measures: it walks
+// the start DFA over a sample of the caller's streams on the host (state 1 = "A alone" from the second symbol on,
+// as in every stream of an unanchored ruleset), renumbers the states by visit count (0 and 1 stay) and replaces the
+// DEVICE copy of the tables.  The host image -- and therefore execution-image files -- is unchanged: renumbering
+// DFA states changes no result, only where a row lives.
+static int calibrate_part(rfb_ctx *ctx, Part &p, const uint8_t *sample, size_t n_streams, size_t pitch, size_t n_steps,
+                          uint64_t *symbols, double *hot_fraction) {
+    const Image &im = p.img;
+    if (!im.ok || !im.h.accel || im.dfa.n < 3) return RFB_OK;
+    const Image::Dfa &D = im.dfa;
+    const uint32_t *cmap = reinterpret_cast<const uint32_t *>(&im.blob[im.h.off_cmap]);
+    uint8_t cls[256];
+    for (int c = 0; c < 256; c++) cls[c] = (uint8_t)(cmap[c] & 0xFFu);
+    std::vector<uint64_t> visits(D.n, 0);
+    for (size_t s = 0; s < n_streams; s++) {
+        const uint8_t *sp = sample + s * pitch;
+        uint32_t d = 1;
+        for (size_t k = 1; k < n_steps; k++) {
+            visits[d]++;
+            d = D.dt[(size_t)d * D.ncls + cls[sp[k]]] & 0x7FFFu;
+            if (d == 0) d = 1;
+        }
+    }
+    std::vector<uint32_t> order(D.n);                  // order[new id] = old id
+    for (uint32_t i = 0; i < D.n; i++) order[i] = i;
+    std::stable_sort(order.begin() + 2, order.end(), [&](uint32_t a, uint32_t b) { return visits[a] > visits[b]; });
+    std::vector<uint32_t> perm(D.n);                   // perm[old id] = new id
+    for (uint32_t i = 0; i < D.n; i++) perm[order[i]] = i;
+    std::vector<uint16_t> dt((size_t)D.n * D.ncls + 8, 0);
+    std::vector<uint32_t> dta((size_t)D.n * D.ncls, 0), mem_ptr(1, 0);
+    std::vector<uint16_t> mem_ids;
+    for (uint32_t nw = 0; nw < D.n; nw++) {
+        const uint32_t o = order[nw];
+        for (uint32_t q = 0; q < D.ncls; q++) {
+            const uint16_t e = D.dt[(size_t)o * D.ncls + q];
+            dt[(size_t)nw * D.ncls + q] = (uint16_t)(perm[e & 0x7FFFu] | (e & 0x8000u));
+            dta[(size_t)nw * D.ncls + q] = D.dta[(size_t)o * D.ncls + q];
+        }
+        for (uint32_t j = D.mem_ptr[o]; j < D.mem_ptr[o + 1]; j++) mem_ids.push_back(D.mem_ids[j]);
+        mem_ptr.push_back((uint32_t)mem_ids.size());
+    }
+    if (mem_ids.empty()) mem_ids.push_back(0);
+    // no scan that reads the old order may still be running
+    CU(ctx, cudaDeviceSynchronize());
+    CU(ctx, cudaMemcpy(p.d_dt, dt.data(), dt.size() * 2, cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpy(p.d_dta, dta.data(), dta.size() * 4, cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpy(p.d_mem_ptr, mem_ptr.data(), mem_ptr.size() * 4, cudaMemcpyHostToDevice));
+    CU(ctx, cudaMemcpy(p.d_mem_ids, mem_ids.data(), mem_ids.size() * 2, cudaMemcpyHostToDevice));
+    p.calibrated = true;
+    const uint32_t hot = lane_hot_rows(im.h, nullptr);
+    uint64_t tot = 0, in_hot = 0;
+    for (uint32_t nw = 0; nw < D.n; nw++) { tot += visits[order[nw]]; if (nw < hot) in_hot += visits[order[nw]]; }
+    if (symbols) *symbols = tot;
+    if (hot_fraction) *hot_fraction = tot ? (double)in_hot / (double)tot : 0.0;
+    return RFB_OK;
+}
+
+static constexpr size_t CALIB_STREAMS = 2048;          // sample size (streams); ~3 M symbols for 1500-byte streams
+static constexpr size_t CALIB_MIN_STREAMS = 8192;      // batches smaller than this are not worth measuring
+
+// `sample`: n_streams rows of n_steps bytes at `pitch` on the HOST
+static int calibrate_nfa(rfb_ctx *ctx, rfb_nfa *nfa, const uint8_t *sample, size_t n_streams, size_t pitch, size_t n_steps) {
+    cudaSetDevice(ctx->device);
+    for (Part &p : nfa->parts) {
+        const int rc = calibrate_part(ctx, p, sample, n_streams, pitch, n_steps, &nfa->calib_symbols, &nfa->calib_hot_fraction);
+        if (rc) return rc;
+    }
+    nfa->calibrated = true;
+    return RFB_OK;
+}
+
+static bool auto_calibrate_enabled() {
+    static const bool on = [] { const char *e = std::getenv("RFB_NO_CALIBRATE"); return !(e && *e && *e != '0'); }();
+    return on;
+}
+
+// first large uniformly strided batch an NFA sees: measure on a strided sample of it (host or device memory)
+static int maybe_calibrate(rfb_ctx *ctx, const rfb_nfa *nfa_c, const rfb_batch *b, bool host) {
+    rfb_nfa *nfa = const_cast<rfb_nfa *>(nfa_c);       // the device tables are a cache of the NFA, not part of its value
+    if (nfa->calibrated || !auto_calibrate_enabled() || b->offsets || b->steps || b->n_streams < CALIB_MIN_STREAMS || b->n_steps < 64) return RFB_OK;
+    const size_t n = CALIB_STREAMS, step = (size_t)(b->n_streams / n);
+    if (host) return calibrate_nfa(ctx, nfa, b->data, n, (size_t)b->stride * step, b->n_steps);
+    std::vector<uint8_t> sample(n * (size_t)b->n_steps);
+    cudaSetDevice(ctx->device);
+    CU(ctx, cudaMemcpy2D(sample.data(), b->n_steps, b->data, (size_t)b->stride * step, b->n_steps, n, cudaMemcpyDeviceToHost));
+    return calibrate_nfa(ctx, nfa, sample.data(), n, b->n_steps, b->n_steps);
+}
+
+int rfb_nfa_calibrate(rfb_ctx *ctx, rfb_nfa *nfa, const rfb_batch *sample) {
+    if (!ctx || !nfa || !sample) return fail(ctx, RFB_E_INVALID, "NULL argument");
+    if (nfa->ctx != ctx) return fail(ctx, RFB_E_INVALID, "nfa belongs to another context");
+    if (sample->offsets || sample->steps) return fail(ctx, RFB_E_UNSUPPORTED, "rfb_nfa_calibrate takes a uniformly strided host batch");
+    const int rc = check_batch(ctx, sample, true);
+    if (rc) return rc;
+    if (sample->n_streams == 0 || sample->n_steps < 2) return RFB_OK;
+    return calibrate_nfa(ctx, nfa, sample->data, (size_t)sample->n_streams, (size_t)sample->stride, sample->n_steps);
+}
+
+int rfb_nfa_calibration(const rfb_nfa *nfa, uint64_t *sample_symbols, double *hot_fraction) {
+    if (!nfa) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    if (sample_symbols) *sample_symbols = nfa->calibrated ? nfa->calib_symbols : 0;
+    if (hot_fraction) *hot_fraction = nfa->calibrated ? nfa->calib_hot_fraction : 0.0;
+    return nfa->calibrated ? 1 : 0;
+}
+
 // ---- the scan ----------------------------------------------------------------------------------------
 static int check_batch(rfb_ctx *ctx, const rfb_batch *b, bool host) {
     if (!b) return fail(ctx, RFB_E_INVALID, "batch is NULL");
     if (b->n_streams > 0xFFF00000ull) return fail(ctx, RFB_E_INVALID, "n_streams exceeds 2^32 - 2^20 (stream ids and the fetch counter are 32-bit)");
     if (b->n_streams && !b->data && b->data_bytes) return fail(ctx, RFB_E_INVALID, "data is NULL");
     if ((b->state_in || b->state_out) && (b->state_cap == 0 || b->state_cap > 255)) return fail(ctx, RFB_E_INVALID, "state_cap must be 1..255 when state_in/state_out are used");
-    if (host) {  // host pointers can be bounds-checked
-        for (uint64_t s = 0; s < b->n_streams; s++) {
-            const uint64_t off = b->offsets ? b->offsets[s] : s * b->stride;
-            const uint64_t len = b->steps ? b->steps[s] : b->n_steps;
-            if (off + len > b->data_bytes) return fail(ctx, RFB_E_INVALID, "stream " + std::to_string(s) + " extends past data_bytes");
+    // every comparison below is written so that it cannot wrap (a huge offset or stride must fail, not pass)
+    auto fits = [&](uint64_t off, uint64_t len) { return len <= b->data_bytes && off <= b->data_bytes - len; };
+    if (!b->offsets && !b->steps) {
+        if (b->n_streams) {
+            const uint64_t last = b->n_streams - 1;
+            if (last && b->stride > (UINT64_MAX - b->n_steps) / last) return fail(ctx, RFB_E_INVALID, "stride * n_streams overflows");
+            if (!fits(last * b->stride, b->n_steps)) return fail(ctx, RFB_E_INVALID, "streams extend past data_bytes");
         }
-    } else if (!b->offsets && !b->steps && b->n_streams) {
-        if ((b->n_streams - 1) * b->stride + b->n_steps > b->data_bytes) return fail(ctx, RFB_E_INVALID, "streams extend past data_bytes");
+    } else if (host) {  // host arrays can be read here; device arrays are the caller's responsibility
+        for (uint64_t s = 0; s < b->n_streams; s++) {
+            const uint64_t len = b->steps ? b->steps[s] : b->n_steps;
+            uint64_t off;
+            if (b->offsets) off = b->offsets[s];
+            else if (s && b->stride > UINT64_MAX / s) return fail(ctx, RFB_E_INVALID, "stride * n_streams overflows");
+            else off = s * b->stride;
+            if (!fits(off, len)) return fail(ctx, RFB_E_INVALID, "stream " + std::to_string(s) + " extends past data_bytes");
+        }
     }
     return RFB_OK;
 }
@@ -608,6 +734,7 @@ int rfb_scan_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
     int rc = check_batch(ctx, b, false);
     if (rc) return rc;
     if ((flags & RFB_SCAN_SORT_RECORDS) && (flags & RFB_SCAN_ASYNC)) return fail(ctx, RFB_E_UNSUPPORTED, "RFB_SCAN_SORT_RECORDS needs the record count: not available with RFB_SCAN_ASYNC");
+    if (!(flags & RFB_SCAN_FORCE_WARP) && (rc = maybe_calibrate(ctx, nfa, b, false)) != RFB_OK) return rc;
     cudaSetDevice(ctx->device);
     (void)cudaGetLastError();   // a stale error of an unrelated earlier call must not be blamed on this launch
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
@@ -651,7 +778,9 @@ static uint64_t plan_chunks(const rfb_nfa *nfa, const rfb_batch *b, uint32_t fla
         n_chunks = std::min<uint64_t>(max_chunks, std::max<uint64_t>(1, b->data_bytes / min_bytes));
     }
     *n_chunks_out = n_chunks;
-    return n_chunks > 1 ? ((b->n_streams + n_chunks - 1) / n_chunks + 31) / 32 * 32 : 0;
+    // whole multiples of 128 streams: every chunk boundary is 128-byte aligned whatever the stride, so no cache line of
+    // the kernel's (coherent) input loads straddles a chunk that has not landed yet
+    return n_chunks > 1 ? ((b->n_streams + n_chunks - 1) / n_chunks + 127) / 128 * 128 : 0;
 }
 static int copy_chunks(rfb_ctx *ctx, const rfb_batch *b, uint8_t *d_data, unsigned int *ready, uint64_t n_chunks, uint64_t chunk_streams, cudaStream_t cs) {
     for (uint64_t c = 0; c < n_chunks; c++) {
@@ -678,6 +807,7 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
             for (unsigned int q = 0; q < row[0]; q++)
                 if (row[1 + q] >= nfa->host.n_states) return fail(ctx, RFB_E_INVALID, "state_in of stream " + std::to_string(s) + " holds an id that is not a state of this NFA");
         }
+    if (!(flags & RFB_SCAN_FORCE_WARP) && (rc = maybe_calibrate(ctx, nfa, b, true)) != RFB_OK) return rc;
     cudaSetDevice(ctx->device);
     (void)cudaGetLastError();
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
@@ -787,6 +917,7 @@ int rfb_scan_submit(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
     if (b->offsets || b->steps || b->state_in || b->state_out)
         return fail(ctx, RFB_E_UNSUPPORTED, "rfb_scan_submit takes uniformly strided batches without per-stream lengths or resumed state");
     if (ctx->slots_busy == 2) return fail(ctx, RFB_E_INVALID, "two batches are in flight: call rfb_scan_wait first");
+    if (ctx->slots_busy == 0 && !(flags & RFB_SCAN_FORCE_WARP) && (rc = maybe_calibrate(ctx, nfa, b, true)) != RFB_OK) return rc;
     cudaSetDevice(ctx->device);
     (void)cudaGetLastError();
     rfb_ctx::Slot &s = ctx->slot[(ctx->slot_head + ctx->slots_busy) & 1];

@@ -67,6 +67,7 @@ struct NfaDev {
     const uint16_t *dfa_act;     // insertion lists: internal id | 0x8000 if another entry follows
     const uint32_t *dfa_mem_ptr; // [dfa_states + 1]: never-materialised members of each DFA state ...
     const uint16_t *dfa_mem_ids; // ... as internal ids
+    uint32_t hot_rows, hot_bytes; // set per launch: rows of dfa_dt staged into shared memory / bytes copied for them (16-byte multiple)
     ImageHeader h;
 };
 
@@ -77,6 +78,7 @@ constexpr int WARP_THREADS = 256;
 constexpr int WARP_LCAP = 512;       // sparse list entries per warp before it switches to bitmap scans
 
 size_t lane_smem_bytes(const ImageHeader &h);
+uint32_t lane_hot_rows(const ImageHeader &h, uint32_t *copy_bytes);
 int lane_ring_cap(const ImageHeader &h);
 size_t warp_smem_bytes(uint32_t n_states, int warps_per_cta);
 

@@ -424,6 +424,12 @@ int image_build_one(const Nfa &nfa, const ImageOptions &opt, Image &img, std::st
     }
 
     for (uint32_t c = 0; c < 256; c++) cmap[c] = (cmap[c] & 0xFFFFu) | (hfull(c, best_mul, best_sh) << 16);
+    // the lane kernel reads the attention mask and the descriptor of a symbol with ONE 16-byte load (W == 1) / from one
+    // row (W == 2): {class, hash} of cmap[c] as two 32-bit words in the padding of symbol c's mask row
+    for (uint32_t c = 0; c < 256; c++) {
+        const uint32_t cls_hf[2] = {cmap[c] & 0xFFFFu, cmap[c] >> 16};
+        std::memcpy(&mask[c * mstride + (W == 1 ? 8u : 48u)], cls_hf, 8);
+    }
 
     // ---- class membership bitmaps ---------------------------------------------------------------------
     std::vector<uint32_t> memb(std::max<size_t>(1, set_id.size()) * 8, 0);
@@ -643,6 +649,10 @@ int image_verify(const Nfa &nfa, const Image &img, std::string &err) {
             for (uint32_t w = 0; w < W; w++)
                 if (A[w] != (~K[w] | M[w])) { err = "sticky attention mask disagrees with K and M at symbol " + std::to_string(c); return RFB_E_INTERNAL; }
             if ((cmap[c] >> 16) != (((c * h.hash_mul) >> h.hash_shift) & 0xFFu)) { err = "per-symbol hash disagrees with the header at symbol " + std::to_string(c); return RFB_E_INTERNAL; }
+            uint32_t cm_copy[2];
+            std::memcpy(cm_copy, &img.blob[h.off_mask + c * mstride + (W == 1 ? 8u : 48u)], 8);
+            if (cm_copy[0] != (cmap[c] & 0xFFFFu) || cm_copy[1] != (cmap[c] >> 16)) { err = "symbol descriptor copy in the mask row disagrees with cmap at symbol " + std::to_string(c); return RFB_E_INTERNAL; }
+            if ((cmap[c] & 0xFFFFu) >= std::max<uint32_t>(1u, img.dfa.ncls)) { err = "symbol class out of range at symbol " + std::to_string(c); return RFB_E_INTERNAL; }
         }
     }
     if (img.h.accel) {

@@ -19,13 +19,8 @@
 #include "device.h"
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 
-#ifndef RFB_OPEN_REPS
-#define RFB_OPEN_REPS 1      // measured: see profiles/README.md
-#endif
-#ifndef RFB_DRAIN_REPS
-#define RFB_DRAIN_REPS 1
-#endif
 
 namespace rfb {
 
@@ -51,19 +46,24 @@ __device__ __forceinline__ const uint8_t *stream_ptr(const BatchDev &b, unsigned
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void stage_image(uint8_t *dst, const uint8_t *src, uint32_t bytes, uint64_t *bar) {
+__device__ __forceinline__ void stage_image(uint8_t *dst, const uint8_t *src, uint32_t bytes, uint8_t *dst2, const uint8_t *src2, uint32_t bytes2, uint64_t *bar) {
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes + bytes2) : "memory");
         const uint32_t CH = 32768;
         for (uint32_t o = 0; o < bytes; o += CH) {
             uint32_t n = bytes - o < CH ? bytes - o : CH;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          ::"r"(smem_u32(dst + o)), "l"(src + o), "r"(n), "r"(smem_u32(bar)) : "memory");
+        }
+        for (uint32_t o = 0; o < bytes2; o += CH) {
+            uint32_t n = bytes2 - o < CH ? bytes2 - o : CH;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(dst2 + o)), "l"(src2 + o), "r"(n), "r"(smem_u32(bar)) : "memory");
         }
     }
     uint32_t done = 0;
@@ -76,15 +76,33 @@ __device__ __forceinline__ void stage_image(uint8_t *dst, const uint8_t *src, ui
 // ------------------------------------------------------------------------------------------------
 // lane kernel
 // ------------------------------------------------------------------------------------------------
-// ring entries per stream: the largest of 64 / 32 / 16 that fits beside the image (a full ring hands the stream
-// to the general kernel, which is an order of magnitude slower, so capacity is worth the shared memory)
+// Shared memory of a lane-kernel CTA: image | hottest start-DFA rows | per-stream rings | barrier.
+// Ring entries per stream: 32 or 16, whatever fits beside the image (a full ring hands the stream to the general
+// kernel, which is an order of magnitude slower); what is left holds the first rows of the start-DFA table -- the
+// library keeps that table ordered by measured visit frequency (api.cu: calibration), and a row in shared memory
+// costs a bank-conflict-limited gather instead of one L1 wavefront per lane.
 int lane_ring_cap(const ImageHeader &h) {
-    static const int max_cap = [] { const char *e = getenv("RFB_RING_CAP"); const int v = e ? atoi(e) : 64; return v >= 64 ? 64 : v >= 32 ? 32 : 16; }();
+    static const int max_cap = [] { const char *e = getenv("RFB_RING_CAP"); const int v = e ? atoi(e) : 32; return v >= 64 ? 64 : v >= 32 ? 32 : 16; }();
     for (int cap = max_cap; cap >= 16; cap >>= 1)
         if ((size_t)h.blob_bytes + (size_t)cap * LANE_THREADS * 2 + 16 <= MAX_DYN_SMEM) return cap;
     return 0;
 }
-size_t lane_smem_bytes(const ImageHeader &h) { return (size_t)h.blob_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16; }
+// rows of the start-DFA table staged into shared memory, and the (16-byte multiple) bytes copied for them
+uint32_t lane_hot_rows(const ImageHeader &h, uint32_t *copy_bytes) {
+    static const long max_rows = [] { const char *e = getenv("RFB_HOT_ROWS"); return e ? atol(e) : 1L << 30; }();
+    const size_t used = (size_t)h.blob_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16;
+    const size_t avail = used < MAX_DYN_SMEM ? (MAX_DYN_SMEM - used) & ~(size_t)15 : 0;
+    const size_t row = (size_t)std::max<uint32_t>(1u, h.dfa_ncls) * 2;
+    size_t rows = std::min<size_t>(std::max<uint32_t>(1u, h.dfa_states), avail / row);
+    if ((long)rows > max_rows) rows = (size_t)std::max<long>(0, max_rows);
+    if (copy_bytes) *copy_bytes = (uint32_t)((rows * row + 15) & ~(size_t)15);
+    return (uint32_t)rows;
+}
+size_t lane_smem_bytes(const ImageHeader &h) {
+    uint32_t hot_bytes = 0;
+    lane_hot_rows(h, &hot_bytes);
+    return (size_t)h.blob_bytes + hot_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16;
+}
 
 // explicit shared-window accesses: 32-bit shared addresses never go through generic-pointer conversion.
 // Table loads are plain asm (read-only data, the compiler may schedule them freely); ring accesses are volatile.
@@ -143,6 +161,39 @@ __device__ __noinline__ void carry_state(const unsigned int *src, unsigned int *
     for (uint32_t i = 0; i < n && i < cap; i++) dst[1 + i] = src[1 + i];
 }
 
+// input chunks: plain (coherent) 16-byte loads -- in the chunk-gated host path the copy engine is still writing LATER
+// chunks of the same buffer while the kernel runs, so the non-coherent (.nc) path is not used for the batch; chunk
+// boundaries are 128-byte aligned (api.cu: plan_chunks), so no cache line ever straddles a chunk that has not landed
+__device__ __forceinline__ uint4 ld_in(const uint8_t *p) {
+    uint4 v; asm("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p)); return v;
+}
+// first loads of a stream: ordered after the acquire of the chunk's arrival counter
+__device__ __forceinline__ uint4 ld_in_ordered(const uint8_t *p) {
+    uint4 v; asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
+    unsigned int v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+// start-DFA entry, sign-extended: negative <=> the transition has an insertion list
+__device__ __forceinline__ int ldg_s16(const uint16_t *p) { int v; asm("ld.global.nc.s16 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+__device__ __forceinline__ int lds_s16(uint32_t a) { int v; asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+
+#ifndef RFB_QUIET_REPS
+#define RFB_QUIET_REPS 1     // quiet runs per iteration of the flat loop
+#endif
+#ifndef RFB_QUIET_STEPS
+#define RFB_QUIET_STEPS 16   // symbols per quiet run (<= 16: one input chunk)
+#endif
+
+// v >>= 8 * nb (nb in 0..15), branch-free
+__device__ __forceinline__ void shr_bytes(uint4 &v, uint32_t nb) {
+    const bool b8 = (nb & 8u) != 0, b4 = (nb & 4u) != 0;
+    uint32_t x = b8 ? v.z : v.x, y = b8 ? v.w : v.y, z = b8 ? 0u : v.z, w = b8 ? 0u : v.w;
+    x = b4 ? y : x; y = b4 ? z : y; z = b4 ? w : z; w = b4 ? 0u : w;
+    const uint32_t sh = (nb & 3u) * 8u;
+    v.x = __funnelshift_r(x, y, sh); v.y = __funnelshift_r(y, z, sh); v.z = __funnelshift_r(z, w, sh); v.w = w >> sh;
+}
+
 template <int W, int RING_CAP>
 __global__ void __launch_bounds__(LANE_THREADS, 1)
 scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
@@ -152,11 +203,9 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     constexpr uint32_t RING = RING_CAP * ROW;
     constexpr uint32_t RMASK = RING - 1;
     constexpr uint32_t NONE = 0xFFFFFFFFu;
-    // an iteration of the flat loop: up to open_reps symbol steps for a lane with nothing to drain, then up to
-    // drain_reps work items for a lane that has some
-    constexpr int open_reps = RFB_OPEN_REPS, drain_reps = RFB_DRAIN_REPS;
-    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + h.blob_bytes + RING);
-    stage_image(smem, nfa.blob, h.blob_bytes, bar);
+    // shared memory: image | first hot_rows rows of the start-DFA table | rings | barrier
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + h.blob_bytes + nfa.hot_bytes + RING);
+    stage_image(smem, nfa.blob, h.blob_bytes, smem + h.blob_bytes, reinterpret_cast<const uint8_t *>(nfa.dfa_dt), nfa.hot_bytes, bar);
 
     // 32-bit shared-window addresses of the staged tables and of this lane's ring
     // ptxas re-derives the shared window base (S2R CgaCtaId + LEA) and threadIdx at every use to save a register;
@@ -166,28 +215,35 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     constexpr uint32_t OFF_CMAP = 256u * 32u * W, OFF_SDESC = OFF_CMAP + 1024u, OFF_TAB = OFF_SDESC + 64u * W * 4u;
     const uint32_t mask_s = sbase, cmap_s = sbase + OFF_CMAP, sdesc_s = sbase + OFF_SDESC, tab_s = sbase + OFF_TAB;
     const uint32_t memb_s = sbase + h.off_memb;
-    const uint32_t lb = __shfl_sync(0xffffffffu, sbase + h.blob_bytes + threadIdx.x * 2, threadIdx.x & 31);   // ring entry at byte offset o: lb + o; bank-conflict free
+    const uint32_t hot_s = sbase + h.blob_bytes, hot_rows = nfa.hot_rows;
+    const uint32_t lb = __shfl_sync(0xffffffffu, sbase + h.blob_bytes + nfa.hot_bytes + threadIdx.x * 2, threadIdx.x & 31);   // ring entry at byte offset o: lb + o; bank-conflict free
     const uint32_t gbase = h.gbase, nsb = h.nsb;
     const uint32_t nbm = (1u << h.bucket_bits) - 1u;
     const uint32_t acc_base = h.acc_base, n_acc = h.n_acc, ncls = h.dfa_ncls;
     const uint16_t *__restrict__ dfa_dt = nfa.dfa_dt;
-    const bool accel = h.accel != 0;
+    const uint32_t abit = h.accel ? 1u : 0u;            // without a start DFA the table is one inert entry and d stays 0
     constexpr uint32_t MSTRIDE = 32u * W;
+    constexpr uint32_t CM_OFF = W == 1 ? 8u : 48u;      // {class, hash} of symbol c in the padding of its mask row
 
-    // One THREAD per stream, and every thread walks its stream at its own pace: the loop below is flat.  An
-    // iteration either opens the next symbol step of the lane's stream (symbol fetch, start-DFA step, sticky
-    // masks) or drains ONE work item of the open step (a start-DFA insertion, a member of the current set, a row
-    // of a firing sticky state) with one edge-table lookup and one insertion.  Lanes of a warp are at different
-    // symbols and different streams; a lane that finishes a stream takes the next one from a global counter, so
-    // busy and quiet streams balance automatically.
+    // One THREAD per stream, every thread at its own pace.  An iteration of the flat loop offers each lane three
+    // blocks and the lane takes the ones its state asks for:
+    //   QUIET  a lane whose step is closed and whose transient set is empty runs up to 16 symbols straight from its
+    //          input registers (bytes at static positions, no branches: a step that must not count is computed and
+    //          discarded) with one start-DFA lookup and one sticky attention test per symbol -- the state in which
+    //          most symbols of most streams are scanned; the run stops in front of the first symbol that needs
+    //          anything else (flagged DFA transition, sticky state firing or dying);
+    //   OPEN   closes the stream / takes the next one / opens the next symbol step the general way;
+    //   DRAIN  one work item of the open step (an entry of a start-DFA insertion list, a member of the current
+    //          set, a row of a firing sticky state): one edge-table lookup and one insertion.
+    // A step is closed (current <= next, Design/FPGA.v:733-737) as soon as its last item is drained.
     uint64_t P0 = 0, P1 = 0;                            // sticky set (P1 unused when W == 1)
     uint32_t rp = 0, re = 0, wp = 0;                    // ring byte offsets: next read, end of current set, next write
     uint32_t filt = 0;                                  // 32-bit membership filter of this step's new entries
     uint32_t d = 0;                                     // start-DFA state: 0 = A not active yet, 1 = A alone
-    uint32_t b0 = 0, b1 = 0, b2 = 0, b3 = 0;            // remaining bytes of the current 16-byte chunk, next byte in b0[7:0]
-    uint4 pre = make_uint4(0, 0, 0, 0);                 // the chunk after it
-    uint32_t bufn = 0;
-    const uint8_t *nextp = nullptr, *endp = nullptr;
+    uint4 cur = make_uint4(0, 0, 0, 0);                 // the next nv bytes of the stream, next symbol in cur.x[7:0]
+    uint4 pre = make_uint4(0, 0, 0, 0);                 // the aligned 16-byte chunk after them
+    uint32_t nv = 0;
+    const uint8_t *np = nullptr, *lastc = nullptr;      // address of pre; address of the stream's last chunk
     uint32_t sid = 0, k = 0, nsteps = 0;
     uint32_t c = 0, hf = 0, hc = 0;                     // symbol of the open step and its hashes
     uint32_t x = NONE;                                  // next entry of a pending start-DFA insertion list
@@ -195,112 +251,144 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     uint32_t idx = 0;
     bool have = false, pend = false, walking = false, ovf = false;
     bool firing = false;                                // (i0 | i1 | i2 | i3) != 0
+    bool calm = false;                                  // the lane's last symbol needed nothing: a quiet run is worth trying
 
-    bool done = false;
+// step k is complete: current <= next.  A full ring hands the stream to the general kernel: S_{k-1} was fully
+// examined, that kernel re-runs the stream and reports from step k on (after the last step there is nothing left
+// to report, but the caller may want S_{n_steps}: only that kernel has it)
+#define RFB_CLOSE_STEP()                                                                   \
+    do {                                                                                   \
+        re = wp; filt = 0; k++;                                                            \
+        if (ovf) {                                                                         \
+            if (k < nsteps || batch.state_out) {                                           \
+                const unsigned int slot_ = atomicAdd(&out.g->n_rescan, 1u);                \
+                out.rescan[slot_] = make_uint2(sid, k);                                    \
+            }                                                                              \
+            have = false; ovf = false;                                                     \
+        }                                                                                  \
+    } while (0)
+
     for (;;) {
 #pragma unroll 1
-        for (int rep = 0; rep < open_reps && !pend; rep++) {
-            if (have) {   // ---- close step k: current <= next (Design/FPGA.v:733-737) ----
-                re = wp; filt = 0;
-                k++;
-                if (ovf) {   // the ring filled up while S_{k} was being built: S_{k-1} was fully examined, the general
-                             // kernel re-runs the stream and reports from step k on (after the last step there is
-                             // nothing left to report, but the caller may want S_{n_steps}: only that kernel has it)
-                    if (k < nsteps || batch.state_out) {
-                        const unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
-                        out.rescan[slot] = make_uint2(sid, k);
+        for (int rep = 0; rep < RFB_QUIET_REPS; rep++) {
+            if (have && nv == 0u) {                      // next chunk
+                cur = pre; nv = 16u;
+                if (np < lastc) { np += 16; pre = ld_in(np); }
+            }
+            // ---- QUIET run: to the end of the bytes at hand, or to the first symbol with an event ----
+            if (have && !pend && calm && rp == re && k < nsteps) {
+                d = max(d, (uint32_t)P0 & abit);         // A entered the set (it never leaves): 0 -> 1
+                const uint32_t plo = (uint32_t)P0, phi = (uint32_t)(P0 >> 32), qlo = (uint32_t)P1, qhi = (uint32_t)(P1 >> 32);
+                // a lane whose only sticky state is A (whose edges the start DFA follows) has nothing to attend to
+                const bool needmask = ((plo & ~abit) | phi | qlo | qhi) != 0u;
+                const uint32_t n = min(nv, nsteps - k);
+                uint32_t cnt = 0;
+#pragma unroll
+                for (int J = 0; J < RFB_QUIET_STEPS; J++) {
+                    if ((uint32_t)J >= n) break;
+                    const uint32_t w = J < 4 ? cur.x : J < 8 ? cur.y : J < 12 ? cur.z : cur.w;
+                    const uint32_t cc = (w >> (8 * (J & 3))) & 0xFFu;
+                    const uint32_t cls = lds32(cmap_s + cc * 4) & 0xFFFFu;
+                    uint32_t t = 0;
+                    if (needmask) {
+                        const uint32_t mrow = mask_s + cc * MSTRIDE;
+                        if (W == 1) { const uint2 a = lds64(mrow); t = (plo & a.x) | (phi & a.y); }
+                        else { const uint4 a = lds128(mrow); t = (plo & a.x) | (phi & a.y) | (qlo & a.z) | (qhi & a.w); }
                     }
-                    have = false; ovf = false;
-                } else if (k == nsteps) {
-                    if (batch.state_out)
-                        lane_export_state(nfa.orig_of_id, nfa.dfa_mem_ptr, nfa.dfa_mem_ids, batch.state_out + (size_t)sid * (1u + batch.state_cap),
-                                          batch.state_cap, batch.state_append != 0, P0, P1, lb, rp, re, ROW, RMASK, d);
-                    have = false;
+                    const uint32_t at = d * ncls + cls;
+                    const int e = d < hot_rows ? lds_s16(hot_s + at * 2) : ldg_s16(dfa_dt + at);
+                    if ((t | ((uint32_t)e & 0x80000000u)) != 0u) break;   // the OPEN block takes this symbol
+                    d = (uint32_t)e;
+                    cnt = (uint32_t)(J + 1);
                 }
+                k += cnt; nv -= cnt;
+                calm = cnt != 0u;
+                if (nv && cnt) shr_bytes(cur, cnt);
+            }
+        }
+        // ---- OPEN ----
+        if (!pend && !(have && nv == 0u && k != nsteps)) {
+            if (have && k == nsteps) {                   // stream finished
+                if (batch.state_out)
+                    lane_export_state(nfa.orig_of_id, nfa.dfa_mem_ptr, nfa.dfa_mem_ids, batch.state_out + (size_t)sid * (1u + batch.state_cap),
+                                      batch.state_cap, batch.state_append != 0, P0, P1, lb, rp, re, ROW, RMASK, d);
+                have = false;
             }
             if (!have) {   // ---- next stream ----
                 for (;;) {
                     sid = atomicAdd(&out.g->next_stream, 1u);
                     if (sid >= batch.n_streams) break;
                     nsteps = batch.steps ? batch.steps[sid] : batch.n_steps;
-                    if (nsteps) break;
-                    if (batch.state_out && !batch.state_append)
-                        carry_state(batch.state_in ? batch.state_in + (size_t)sid * (1u + batch.state_cap) : nullptr,
-                                    batch.state_out + (size_t)sid * (1u + batch.state_cap), batch.state_cap);
-                }
-                if (sid >= batch.n_streams) { done = true; break; }   // this lane is done
-                if (batch.steps && batch.count_symbols) atomicAdd(&out.g->n_symbols, (unsigned long long)nsteps);
-                if (batch.chunk_streams) {   // host path: wait until the H2D copy of this stream's chunk has landed
-                    const unsigned int need = sid / batch.chunk_streams + 1u;
-                    while (*reinterpret_cast<const volatile unsigned int *>(batch.ready) < need) __nanosleep(256);
-                }
-                P0 = 0; P1 = 0; rp = 0; re = 0; wp = 0; filt = 0; d = 0; k = 0;
-                if (batch.state_in) {   // resume: the stream's active set as left by an earlier call
-                    const unsigned int *stt = batch.state_in + (size_t)sid * (1u + batch.state_cap);
-                    const uint32_t ns = stt[0] <= batch.state_cap ? stt[0] : 0u;   // an overflow mark cannot be resumed: treated as empty (rfb_scan rejects it)
-                    bool fits = true;
-                    for (uint32_t q = 0; q < ns; q++) {
-                        if (stt[1 + q] >= nfa.n_ref_states) continue;                // not a state: ignored
-                        const uint32_t id = nfa.id_of_orig[stt[1 + q]];
-                        if (id == 0xFFFFFFFFu) continue;          // a state of another part
-                        if (id < nsb) { if (W == 1 || id < 64) P0 |= 1ull << (id & 63); else P1 |= 1ull << (id & 63); }
-                        else if (((wp + ROW) & RMASK) == rp) fits = false;
-                        else { ring_st(lb + wp, id); wp = (wp + ROW) & RMASK; }
-                    }
-                    re = wp;
-                    if (!fits) {   // more transient members than the ring holds: the general kernel takes the whole stream
-                        const unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
-                        out.rescan[slot] = make_uint2(sid, 0u);
+                    if (nsteps == 0) {
+                        if (batch.state_out && !batch.state_append)
+                            carry_state(batch.state_in ? batch.state_in + (size_t)sid * (1u + batch.state_cap) : nullptr,
+                                        batch.state_out + (size_t)sid * (1u + batch.state_cap), batch.state_cap);
                         continue;
                     }
-                } else if (h.start_id < nsb) {                                        // Design/FPGA.v:146-147
-                    if (W == 1 || h.start_id < 64) P0 = 1ull << (h.start_id & 63); else P1 = 1ull << (h.start_id & 63);
-                } else { ring_st(lb, h.start_id); re = ROW; wp = ROW; }
-                // input: aligned 16-byte chunks kept in registers, the first one shifted to the stream's first byte
-                const uint8_t *sp = stream_ptr(batch, sid);
-                endp = sp + nsteps;
-                const uint8_t *b16 = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15);
-                const uint32_t off = (uint32_t)(sp - b16);
-                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(b16));
-                b0 = v.x; b1 = v.y; b2 = v.z; b3 = v.w;
-                for (uint32_t q = 0; q < off; q++) {    // once per stream; off == 0 for aligned batches
-                    b0 = __funnelshift_r(b0, b1, 8); b1 = __funnelshift_r(b1, b2, 8); b2 = __funnelshift_r(b2, b3, 8); b3 >>= 8;
+                    if (batch.steps && batch.count_symbols) atomicAdd(&out.g->n_symbols, (unsigned long long)nsteps);
+                    if (batch.chunk_streams) {   // host path: wait until the H2D copy of this stream's chunk has landed
+                        const unsigned int need = sid / batch.chunk_streams + 1u;
+                        while (ld_acquire(batch.ready) < need) __nanosleep(256);
+                    }
+                    P0 = 0; P1 = 0; rp = 0; re = 0; wp = 0; filt = 0; d = 0; k = 0;
+                    if (batch.state_in) {   // resume: the stream's active set as left by an earlier call
+                        const unsigned int *stt = batch.state_in + (size_t)sid * (1u + batch.state_cap);
+                        const uint32_t ns = stt[0] <= batch.state_cap ? stt[0] : 0u;   // an overflow mark cannot be resumed: treated as empty (rfb_scan rejects it)
+                        bool fits = true;
+                        for (uint32_t q = 0; q < ns; q++) {
+                            if (stt[1 + q] >= nfa.n_ref_states) continue;                // not a state: ignored
+                            const uint32_t id = nfa.id_of_orig[stt[1 + q]];
+                            if (id == 0xFFFFFFFFu) continue;          // a state of another part
+                            if (id < nsb) { if (W == 1 || id < 64) P0 |= 1ull << (id & 63); else P1 |= 1ull << (id & 63); }
+                            else if (((wp + ROW) & RMASK) == rp) fits = false;
+                            else { ring_st(lb + wp, id); wp = (wp + ROW) & RMASK; }
+                        }
+                        re = wp;
+                        if (!fits) {   // more transient members than the ring holds: the general kernel takes the whole stream
+                            const unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
+                            out.rescan[slot] = make_uint2(sid, 0u);
+                            continue;
+                        }
+                    } else if (h.start_id < nsb) {                                        // Design/FPGA.v:146-147
+                        if (W == 1 || h.start_id < 64) P0 = 1ull << (h.start_id & 63); else P1 = 1ull << (h.start_id & 63);
+                    } else { ring_st(lb, h.start_id); re = ROW; wp = ROW; }
+                    break;
                 }
-                bufn = 16 - off;
-                nextp = b16 + 16;
-                if (nextp < endp) pre = __ldg(reinterpret_cast<const uint4 *>(nextp));
-                nextp += 16;
-                have = true;
+                if (sid >= batch.n_streams) break;       // this lane is done
+                // input: aligned 16-byte chunks; the first one is shifted down to the stream's first byte
+                const uint8_t *sp = stream_ptr(batch, sid);
+                np = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15);
+                lastc = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(sp + (nsteps - 1u)) & ~(uintptr_t)15);
+                const uint32_t off = (uint32_t)(sp - np);
+                cur = ld_in_ordered(np);
+                shr_bytes(cur, off);
+                nv = 16u - off;
+                if (np < lastc) { np += 16; pre = ld_in_ordered(np); }
+                have = true; calm = false;
             }
             // ---- open step k: next symbol ----
-            if (bufn == 0) {
-                b0 = pre.x; b1 = pre.y; b2 = pre.z; b3 = pre.w; bufn = 16;
-                if (nextp < endp) pre = __ldg(reinterpret_cast<const uint4 *>(nextp));
-                nextp += 16;
-            }
-            c = b0 & 0xFFu;
-            b0 = __funnelshift_r(b0, b1, 8); b1 = __funnelshift_r(b1, b2, 8); b2 = __funnelshift_r(b2, b3, 8); b3 >>= 8;
-            bufn--;
-            const uint32_t cm = lds32(cmap_s + c * 4);  // per-symbol descriptor: start-DFA class | hash << 16
-            hf = cm >> 16;                              // symbol hash; a row uses its low bits
-            hc = hf & nbm;
+            c = cur.x & 0xFFu;
+            cur.x = __funnelshift_r(cur.x, cur.y, 8); cur.y = __funnelshift_r(cur.y, cur.z, 8); cur.z = __funnelshift_r(cur.z, cur.w, 8); cur.w >>= 8;
+            nv--;
+            const uint32_t mrow = mask_s + c * MSTRIDE;
+            const uint4 a = lds128(mrow);               // attention masks (W == 1: | start-DFA class | symbol hash)
+            uint32_t cls;
+            if (W == 1) { cls = a.z; hf = a.w; }
+            else { const uint2 ch = lds64(mrow + CM_OFF); cls = ch.x; hf = ch.y; }
+            hc = hf & nbm;                              // a hashed row uses the low bits of the symbol hash
             // start DFA: one lookup steps all the never-materialised successors of the always-active state A
-            if (accel) {
-                d = max(d, (uint32_t)P0 & 1u);          // A entered the set (it never leaves): 0 -> 1
-                const uint32_t at = d * ncls + (cm & 0xFFu);
-                const uint32_t e = __ldg(dfa_dt + at);
-                d = e & 0x7FFFu;
-                if (e & 0x8000u) x = __ldg(nfa.dfa_dta + at);   // sticky / accepting / untracked successors to insert
+            {
+                d = max(d, (uint32_t)P0 & abit);
+                const uint32_t at = d * ncls + cls;
+                const int e = d < hot_rows ? lds_s16(hot_s + at * 2) : ldg_s16(dfa_dt + at);
+                d = (uint32_t)e & 0x7FFFu;
+                if (e < 0) x = __ldg(nfa.dfa_dta + at);   // sticky / accepting / untracked successors to insert
             }
             // sticky states: survivors P & K[c]; those in P & M[c] fire their rows
             {
-                const uint32_t mrow = mask_s + c * MSTRIDE;
                 bool attn;
-                if (W == 1) { const uint2 a2 = lds64(mrow); attn = (((uint32_t)P0 & a2.x) | ((uint32_t)(P0 >> 32) & a2.y)) != 0; }
-                else {
-                    const uint4 a = lds128(mrow);
-                    attn = (((uint32_t)P0 & a.x) | ((uint32_t)(P0 >> 32) & a.y) | ((uint32_t)P1 & a.z) | ((uint32_t)(P1 >> 32) & a.w)) != 0;
-                }
+                if (W == 1) attn = (((uint32_t)P0 & a.x) | ((uint32_t)(P0 >> 32) & a.y)) != 0;
+                else attn = (((uint32_t)P0 & a.x) | ((uint32_t)(P0 >> 32) & a.y) | ((uint32_t)P1 & a.z) | ((uint32_t)(P1 >> 32) & a.w)) != 0;
                 if (attn) {
                     if (W == 1) {
                         const uint4 km = lds128(mrow + 16);
@@ -318,10 +406,11 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                 }
             }
             pend = x != NONE || rp != re || firing;
+            calm = !pend;
+            if (!pend) RFB_CLOSE_STEP();
         }
-        if (done) break;
-#pragma unroll 1
-        for (int rep = 0; rep < drain_reps && pend; rep++) {   // ---- drain work items of the open step ----
+        // ---- DRAIN: one work item of the open step ----
+        if (pend) {
             bool hit = false, look = walking;
             uint32_t t = 0;
             if (!walking) {
@@ -346,8 +435,8 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     else if (i2) { wsel = i2; wbase = 64; i2 &= i2 - 1; }
                     else { wsel = i3; wbase = 96; i3 &= i3 - 1; }
                     firing = (i0 | i1 | i2 | i3) != 0;
-                    const uint32_t d = lds32(sdesc_s + (wbase + (uint32_t)__ffs((int)wsel) - 1u) * 4);
-                    idx = (d & 0xFFFFu) + (hf & (d >> 16));
+                    const uint32_t sd = lds32(sdesc_s + (wbase + (uint32_t)__ffs((int)wsel) - 1u) * 4);
+                    idx = (sd & 0xFFFFu) + (hf & (sd >> 16));
                     look = true;
                 }
             }
@@ -381,12 +470,16 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                 }
             }
             pend = walking || x != NONE || rp != re || firing;
+            if (!pend) RFB_CLOSE_STEP();
         }
     }
+#undef RFB_CLOSE_STEP
 }
 
-cudaError_t launch_scan_lane(const NfaDev &nfa, const BatchDev &batch, const OutDev &out, int n_sms, cudaStream_t stream) {
-    const size_t smem = lane_smem_bytes(nfa.h);
+cudaError_t launch_scan_lane(const NfaDev &nfa_in, const BatchDev &batch, const OutDev &out, int n_sms, cudaStream_t stream) {
+    const size_t smem = lane_smem_bytes(nfa_in.h);
+    NfaDev nfa = nfa_in;
+    nfa.hot_rows = lane_hot_rows(nfa.h, &nfa.hot_bytes);
     unsigned long long want = (batch.n_streams + LANE_THREADS - 1) / LANE_THREADS;
     int grid = (int)(want < (unsigned long long)n_sms ? (want ? want : 1) : (unsigned long long)n_sms);
     const int cap = lane_ring_cap(nfa.h);

@@ -324,6 +324,24 @@ class Nfa:
         _check(self._L.rfb_scan_device(self.ctx._h, self._h, C.byref(b), flags, cuda_stream, C.byref(r)), self.ctx._h)
         return r
 
+    def calibrate(self, data, n_streams, n_steps, stride):
+        """Order the start-DFA rows by the visit frequency measured on this HOST sample (rfb_nfa_calibrate).  The
+        library does this by itself on the first large batch; calling it explicitly picks the sample and the moment."""
+        data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        b = rfb_batch()
+        b.data = data.ctypes.data if data.size else None
+        b.data_bytes = data.size
+        b.n_streams = n_streams
+        b.stride = stride
+        b.n_steps = n_steps
+        _check(self._L.rfb_nfa_calibrate(self.ctx._h, self._h, C.byref(b)), self.ctx._h)
+
+    def calibration(self):
+        """(calibrated?, symbols of the sample, share of its start-DFA lookups served from shared memory)."""
+        n, f = C.c_uint64(), C.c_double()
+        rc = self._L.rfb_nfa_calibration(self._h, C.byref(n), C.byref(f))
+        return bool(rc == 1), int(n.value), float(f.value)
+
     def fpga_cycles(self, lo, hi, trace_entries):
         """The testbench's "Total no. cycles" (testbench_BLK_Mem.sv:52,84) for an M-entry (lo, hi) trace pair."""
         lo = np.ascontiguousarray(lo, dtype=np.uint8)

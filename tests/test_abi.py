@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     assert sorted(_lib.SIGNATURES) == names, "python binding and header disagree"
-    assert _lib.load().rfb_abi_version() == 3
+    assert _lib.load().rfb_abi_version() == 4
 
 
 def test_struct_layouts_match_header():

@@ -7,6 +7,7 @@
 #include "host.h"
 #include <algorithm>
 #include <cstdio>
+#include <functional>
 #include <cstdlib>
 #include <set>
 #include <vector>
@@ -124,6 +125,17 @@ int main(int argc, char **argv) {
         Stats &s = st[t];
         printf("%s: per symbol: t2hits %.3f entries %.3f lookups %.3f indirect %.3f class %.3f pushes %.3f attn %.3f inj %.3f sticky %.2f maxlist %.0f\n", t ? "hi" : "lo", s.t2hits / s.symbols,
                s.entries / s.symbols, s.lookups / s.symbols, s.indirect / s.symbols, s.cls / s.symbols, s.pushes / s.symbols, s.attn / s.symbols, s.inj / s.symbols, s.sticky / s.symbols, s.maxlist);
+    }
+    { std::vector<uint64_t> sh = dhist; std::sort(sh.begin(), sh.end(), std::greater<uint64_t>()); uint64_t tot = 0, cum = 0; for (auto v : sh) tot += v; size_t i = 0;
+      for (size_t H : {16, 64, 128, 256, 325, 512, 700, 1024, 2048, 4096}) { for (; i < H && i < sh.size(); i++) cum += sh[i]; printf("DFA lookups landing in the %zu most visited states: %.4f\n", H, tot ? (double)cum / tot : 0.0); } }
+    {   // static prior: visits under i.i.d. uniform bytes; how much of the REAL traffic do its top-H states cover?
+        const uint32_t *cmap = (const uint32_t *)&img.blob[h.off_cmap]; const Image::Dfa &D = img.dfa;
+        std::vector<uint64_t> prior(D.n, 0); uint32_t d = 1; uint64_t x = 12345;
+        for (int it = 0; it < 4000000; it++) { x = splitmix64(x); const uint32_t c = x & 0xFF; d = D.dt[(size_t)d * D.ncls + (cmap[c] & 0xFF)] & 0x7FFF; if (!d) d = 1; prior[d]++; }
+        std::vector<uint32_t> ord(D.n); for (uint32_t i = 0; i < D.n; i++) ord[i] = i;
+        std::stable_sort(ord.begin(), ord.end(), [&](uint32_t a, uint32_t b) { return prior[a] > prior[b]; });
+        uint64_t tot = 0, cum = 0; for (auto v : dhist) tot += v; size_t i = 0;
+        for (size_t H : {64, 325, 700, 1024, 4096}) { for (; i < H && i < ord.size(); i++) cum += ord[i] < dhist.size() ? dhist[ord[i]] : 0; printf("real lookups covered by the top %zu states of the uniform-byte prior: %.4f\n", H, (double)cum / tot); }
     }
     { uint64_t tot = 0, cum = 0; for (auto v : dhist) tot += v; size_t i = 0; for (size_t H : {16, 64, 128, 256, 325, 512, 1024, 2048, 4096}) { for (; i < H && i < dhist.size(); i++) cum += dhist[i]; printf("DFA lookups landing in states < %zu (breadth-first order): %.4f\n", H, tot ? (double)cum / tot : 0.0); } }
     // lock-step warp bound: mean over (warp, symbol) of max over its 32 lanes
