@@ -93,6 +93,7 @@ struct ImageHeader {  // mirrored on the device (passed by value to the kernels)
     // byte offsets of the sections inside the blob (all 16-byte aligned)
     uint32_t off_tab, off_mask, off_memb, off_sdesc;   // sdesc[b] = row base | (row mask << 16) of sticky bit b
     uint32_t off_cmap;      // cmap[c] = start-DFA symbol class | h(c) << 16
+    uint32_t off_look;      // look[c'][sticky_words] (64-bit words): sticky states whose firing can matter when the NEXT symbol is c
     // start DFA of the always-active sticky state (bit 0), tables in global memory; accel == 0: absent
     uint32_t accel, dfa_ncls, dfa_states;
     uint32_t blob_bytes;

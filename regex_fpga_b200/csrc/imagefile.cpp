@@ -8,14 +8,14 @@
 // image goes through.  The sub-NFAs of a cut NFA are not stored: they are re-derived from the stored state groups.
 //
 // Layout (little endian; all counts are element counts):
-//   char magic[8] = "RFBIMG\0\1";  u32 version = 1;  u32 n_parts;  u64 n_entries;  u32 n_states;  u32 reserved = 0
+//   char magic[8] = "RFBIMG\0\1";  u32 version = 2;  u32 n_parts;  u64 n_entries;  u32 n_states;  u32 reserved = 0
 //   u32 entries[n_entries]                                       the .coe contents (row_ptr | transitions | pad)
 //   per part:
 //     u32 n_group;  u32 group[n_group]      reference ids of the part's states, ascending, without state 0
 //                                           (n_group = 0 and n_parts = 1: the whole NFA)
 //     u32 image_ok                          0: this part runs on the general kernel, nothing else is stored for it
 //     u32 header_bytes; ImageHeader         (host.h; header_bytes must equal sizeof(ImageHeader))
-//     u64 n; u8  blob[n]                    mask | cmap | sdesc | tab | memb, staged verbatim into shared memory
+//     u64 n; u8  blob[n]                    mask | cmap | sdesc | tab | memb | look, staged verbatim into shared memory
 //     u64 n; u32 orig_of_id[n]              internal id -> state id of the part
 //     u64 n; u32 id_of_orig[n]              state id of the part -> internal id
 //     u32 n_sticky; u32 n_sticky_dropped; u32 accel_state; u32 n_absorbed
@@ -32,6 +32,7 @@ namespace rfb {
 namespace {
 
 const char MAGIC[8] = {'R', 'F', 'B', 'I', 'M', 'G', 0, 1};
+const uint32_t FILE_VERSION = 2;       // 2: + look-ahead masks (ImageHeader::off_look)
 
 uint64_t fnv1a64(const uint8_t *p, size_t n) {
     uint64_t h = 0xcbf29ce484222325ull;
@@ -68,6 +69,7 @@ int image_validate_structure(const Image &img, uint32_t n_states, std::string &e
     auto bad = [&](const char *what) { err = std::string("execution image is malformed: ") + what; return RFB_E_FORMAT; };
     const size_t B = img.blob.size();
     if (B != h.blob_bytes || B > (1u << 20)) return bad("blob size");
+    if (B + 16 * 1024 * 2 + 64 > 227 * 1024) return bad("tables do not fit one SM's shared memory beside the smallest rings");
     if (h.sticky_words != 1 && h.sticky_words != 2) return bad("sticky words");
     const uint32_t W = h.sticky_words;
     if (h.nsb != 64 * W || h.bucket_bits < 1 || h.bucket_bits > 6 || h.hash_shift > 7) return bad("header fields");
@@ -78,13 +80,21 @@ int image_validate_structure(const Image &img, uint32_t n_states, std::string &e
     if (h.off_sdesc != h.off_cmap + 1024 || !fits(h.off_sdesc, 4ull * h.nsb)) return bad("sdesc section");
     if (h.off_tab != h.off_sdesc + 4 * h.nsb || !fits(h.off_tab, 4ull * h.n_slots)) return bad("tab section");
     if (!fits(h.off_memb, 32ull * (h.n_sets ? h.n_sets : 1)) || h.n_sets > 506) return bad("memb section");
+    if (h.off_look % 8 != 0 || !fits(h.off_look, 256ull * 8 * W)) return bad("look-ahead section");
     if (h.gbase > h.n_slots || h.acc_base > h.n_slots || h.n_acc > h.n_slots - h.acc_base || h.acc_base < h.nsb) return bad("id ranges");
     if (img.orig_of_id.size() != h.n_slots || img.id_of_orig.size() != n_states) return bad("id maps");
     for (uint32_t s = 0; s < n_states; s++) {
         const uint32_t id = img.id_of_orig[s];
         if (id >= h.n_slots || img.orig_of_id[id] != s) return bad("id maps disagree");
     }
-    for (uint32_t o : img.orig_of_id) if (o != 0xFFFFFFFFu && o >= n_states) return bad("orig_of_id");
+    // orig_of_id must be the EXACT inverse of id_of_orig: a second slot naming the same state would let an edge, an
+    // insertion-list entry or a DFA member point at an alias whose row is arbitrary while image_verify(), which maps
+    // ids back through orig_of_id, still sees the right successor
+    for (uint32_t id = 0; id < h.n_slots; id++) {
+        const uint32_t o = img.orig_of_id[id];
+        if (o == 0xFFFFFFFFu) continue;
+        if (o >= n_states || img.id_of_orig[o] != id) return bad("orig_of_id is not the inverse of id_of_orig");
+    }
     if (h.start_id != img.id_of_orig[0]) return bad("start id");
     const uint32_t *tab = reinterpret_cast<const uint32_t *>(&img.blob[h.off_tab]);
     const uint32_t *sdesc = reinterpret_cast<const uint32_t *>(&img.blob[h.off_sdesc]);
@@ -186,7 +196,7 @@ int plan_build(const uint32_t *entries, size_t n_entries, int64_t n_states, cons
 int plan_write(const Plan &plan, const std::string &path, std::string &err) {
     Writer w;
     w.raw(MAGIC, 8);
-    w.u32(1); w.u32((uint32_t)plan.parts.size());
+    w.u32(FILE_VERSION); w.u32((uint32_t)plan.parts.size());
     w.u64(plan.host.entries.size()); w.u32(plan.host.n_states); w.u32(0);
     w.raw(plan.host.entries.data(), plan.host.entries.size() * 4);
     for (const PlanPart &p : plan.parts) {
@@ -236,7 +246,7 @@ int plan_read(const std::string &path, Plan &plan, std::string &err) {
     const uint64_t n_entries = r.u64();
     const uint32_t n_states = r.u32();
     r.u32();
-    if (!r.ok || version != 1) return bad("unsupported version");
+    if (!r.ok || version != FILE_VERSION) return bad("unsupported version");
     if (n_parts == 0 || n_parts > 4096 || n_entries > (1ull << 26) || n_entries * 4 > r.n - r.at) return bad("truncated");
     std::vector<uint32_t> entries((size_t)n_entries);
     r.raw(entries.data(), entries.size() * 4);

@@ -176,6 +176,20 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
 }
 // start-DFA entry, sign-extended: negative <=> the transition has an insertion list
 __device__ __forceinline__ int ldg_s16(const uint16_t *p) { int v; asm("ld.global.nc.s16 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
+// start-DFA entry `at` (= d * ncls + class) of state d: rows below hot_rows from shared memory, the rest from global
+// memory; predicated, no branch
+__device__ __forceinline__ int ld_dfa(uint32_t d, uint32_t hot_rows, uint32_t hot_s, uint32_t at, const uint16_t *base) {
+    int v = 0;   // defined on every path as far as ptxas can tell (the two loads are complementary)
+    asm("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t.reg .u32 sa;\n\t"
+        "setp.lt.u32 p, %1, %2;\n\t"
+        "mad.lo.u32 sa, %4, 2, %3;\n\t"
+        "mad.wide.u32 a, %4, 2, %5;\n\t"
+        "@p ld.shared.s16 %0, [sa];\n\t"
+        "@!p ld.global.nc.s16 %0, [a];\n\t}"
+        : "+r"(v) : "r"(d), "r"(hot_rows), "r"(hot_s), "r"(at), "l"(base));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds16r(uint32_t a) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ int lds_s16(uint32_t a) { int v; asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
 #ifndef RFB_QUIET_REPS
@@ -214,7 +228,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     // fixed-size tables sit at offsets that depend only on W (image.cpp): immediates in the load instructions
     constexpr uint32_t OFF_CMAP = 256u * 32u * W, OFF_SDESC = OFF_CMAP + 1024u, OFF_TAB = OFF_SDESC + 64u * W * 4u;
     const uint32_t mask_s = sbase, cmap_s = sbase + OFF_CMAP, sdesc_s = sbase + OFF_SDESC, tab_s = sbase + OFF_TAB;
-    const uint32_t memb_s = sbase + h.off_memb;
+    const uint32_t memb_s = sbase + h.off_memb, look_s = sbase + h.off_look;
     const uint32_t hot_s = sbase + h.blob_bytes, hot_rows = nfa.hot_rows;
     const uint32_t lb = __shfl_sync(0xffffffffu, sbase + h.blob_bytes + nfa.hot_bytes + threadIdx.x * 2, threadIdx.x & 31);   // ring entry at byte offset o: lb + o; bank-conflict free
     const uint32_t gbase = h.gbase, nsb = h.nsb;
@@ -225,89 +239,95 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     constexpr uint32_t MSTRIDE = 32u * W;
     constexpr uint32_t CM_OFF = W == 1 ? 8u : 48u;      // {class, hash} of symbol c in the padding of its mask row
 
-    // One THREAD per stream, every thread at its own pace.  An iteration of the flat loop offers each lane three
-    // blocks and the lane takes the ones its state asks for:
-    //   QUIET  a lane whose step is closed and whose transient set is empty runs up to 16 symbols straight from its
-    //          input registers (bytes at static positions, no branches: a step that must not count is computed and
-    //          discarded) with one start-DFA lookup and one sticky attention test per symbol -- the state in which
-    //          most symbols of most streams are scanned; the run stops in front of the first symbol that needs
-    //          anything else (flagged DFA transition, sticky state firing or dying);
-    //   OPEN   closes the stream / takes the next one / opens the next symbol step the general way;
-    //   DRAIN  one work item of the open step (an entry of a start-DFA insertion list, a member of the current
-    //          set, a row of a firing sticky state): one edge-table lookup and one insertion.
-    // A step is closed (current <= next, Design/FPGA.v:733-737) as soon as its last item is drained.
+    // One THREAD per stream, every thread at its own pace.  An iteration of the loop offers each lane two blocks and
+    // the lane takes the one its state asks for:
+    //   QUIET  a lane whose transient set is empty runs up to 16 symbols straight from its input registers (bytes at
+    //          static positions) with one start-DFA lookup and, if anybody in the warp holds a sticky state besides A,
+    //          one attention test per symbol -- the state in which most symbols of most streams are scanned; the run
+    //          stops in front of the first symbol that needs anything else (flagged DFA transition, a sticky state
+    //          dying, a sticky state firing into something that can outlive the next symbol);
+    //   STEP   one whole symbol step the general way: finish the stream / take the next one, open the step (start
+    //          DFA, sticky masks), drain every work item of it (entries of a start-DFA insertion list, members of the
+    //          current set, rows of firing sticky states: one edge-table lookup and one insertion each), close it
+    //          (current <= next, Design/FPGA.v:733-737).
+    // All per-step bookkeeping is local to STEP, so the quiet run keeps few registers alive.
     uint64_t P0 = 0, P1 = 0;                            // sticky set (P1 unused when W == 1)
-    uint32_t rp = 0, re = 0, wp = 0;                    // ring byte offsets: next read, end of current set, next write
-    uint32_t filt = 0;                                  // 32-bit membership filter of this step's new entries
+    uint32_t rp = 0, re = 0;                            // ring byte offsets of the current set S_k: [rp, re)
     uint32_t d = 0;                                     // start-DFA state: 0 = A not active yet, 1 = A alone
     uint4 cur = make_uint4(0, 0, 0, 0);                 // the next nv bytes of the stream, next symbol in cur.x[7:0]
     uint4 pre = make_uint4(0, 0, 0, 0);                 // the aligned 16-byte chunk after them
     uint32_t nv = 0;
-    const uint8_t *np = nullptr, *lastc = nullptr;      // address of pre; address of the stream's last chunk
+    const uint8_t *np = nullptr;                        // address of pre
     uint32_t sid = 0, k = 0, nsteps = 0;
-    uint32_t c = 0, hf = 0, hc = 0;                     // symbol of the open step and its hashes
-    uint32_t x = NONE;                                  // next entry of a pending start-DFA insertion list
-    uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;            // firing sticky bits not yet expanded
-    uint32_t idx = 0;
-    bool have = false, pend = false, walking = false, ovf = false;
-    bool firing = false;                                // (i0 | i1 | i2 | i3) != 0
-    bool calm = false;                                  // the lane's last symbol needed nothing: a quiet run is worth trying
-
-// step k is complete: current <= next.  A full ring hands the stream to the general kernel: S_{k-1} was fully
-// examined, that kernel re-runs the stream and reports from step k on (after the last step there is nothing left
-// to report, but the caller may want S_{n_steps}: only that kernel has it)
-#define RFB_CLOSE_STEP()                                                                   \
-    do {                                                                                   \
-        re = wp; filt = 0; k++;                                                            \
-        if (ovf) {                                                                         \
-            if (k < nsteps || batch.state_out) {                                           \
-                const unsigned int slot_ = atomicAdd(&out.g->n_rescan, 1u);                \
-                out.rescan[slot_] = make_uint2(sid, k);                                    \
-            }                                                                              \
-            have = false; ovf = false;                                                     \
-        }                                                                                  \
-    } while (0)
+    bool have = false;
+    bool evt = false;                                   // the quiet run stopped in front of an event: STEP takes that symbol
+    bool done = false;                                  // no stream left for this lane
 
     for (;;) {
-#pragma unroll 1
-        for (int rep = 0; rep < RFB_QUIET_REPS; rep++) {
-            if (have && nv == 0u) {                      // next chunk
-                cur = pre; nv = 16u;
-                if (np < lastc) { np += 16; pre = ld_in(np); }
-            }
-            // ---- QUIET run: to the end of the bytes at hand, or to the first symbol with an event ----
-            if (have && !pend && calm && rp == re && k < nsteps) {
-                d = max(d, (uint32_t)P0 & abit);         // A entered the set (it never leaves): 0 -> 1
-                const uint32_t plo = (uint32_t)P0, phi = (uint32_t)(P0 >> 32), qlo = (uint32_t)P1, qhi = (uint32_t)(P1 >> 32);
-                // a lane whose only sticky state is A (whose edges the start DFA follows) has nothing to attend to
-                const bool needmask = ((plo & ~abit) | phi | qlo | qhi) != 0u;
-                const uint32_t n = min(nv, nsteps - k);
-                uint32_t cnt = 0;
-#pragma unroll
-                for (int J = 0; J < RFB_QUIET_STEPS; J++) {
-                    if ((uint32_t)J >= n) break;
-                    const uint32_t w = J < 4 ? cur.x : J < 8 ? cur.y : J < 12 ? cur.z : cur.w;
-                    const uint32_t cc = (w >> (8 * (J & 3))) & 0xFFu;
-                    const uint32_t cls = lds32(cmap_s + cc * 4) & 0xFFFFu;
-                    uint32_t t = 0;
-                    if (needmask) {
-                        const uint32_t mrow = mask_s + cc * MSTRIDE;
-                        if (W == 1) { const uint2 a = lds64(mrow); t = (plo & a.x) | (phi & a.y); }
-                        else { const uint4 a = lds128(mrow); t = (plo & a.x) | (phi & a.y) | (qlo & a.z) | (qhi & a.w); }
-                    }
-                    const uint32_t at = d * ncls + cls;
-                    const int e = d < hot_rows ? lds_s16(hot_s + at * 2) : ldg_s16(dfa_dt + at);
-                    if ((t | ((uint32_t)e & 0x80000000u)) != 0u) break;   // the OPEN block takes this symbol
-                    d = (uint32_t)e;
-                    cnt = (uint32_t)(J + 1);
-                }
-                k += cnt; nv -= cnt;
-                calm = cnt != 0u;
-                if (nv && cnt) shr_bytes(cur, cnt);
-            }
+        // All 32 lanes stay in the loop until the last one is done, and meet here once per iteration: both blocks are
+        // entered by converged lanes (a lane that leaves a block early waits for the others at the next meeting point
+        // instead of running ahead through private copies of the code).
+        if (__all_sync(0xffffffffu, done)) break;
+        if (have && nv == 0u) {                          // next chunk
+            cur = pre; nv = 16u;
+            if (nsteps - k > 16u) { np += 16; pre = ld_in(np); }     // the stream goes on behind it
         }
-        // ---- OPEN ----
-        if (!pend && !(have && nv == 0u && k != nsteps)) {
+        // ---- QUIET run: to the end of the bytes at hand, or to the first symbol with an event ----
+        if (have && !evt && rp == re && nv != 0u && k < nsteps) {
+            d = max(d, (uint32_t)P0 & abit);             // A entered the set (it never leaves): 0 -> 1
+            const uint32_t plo = (uint32_t)P0, phi = (uint32_t)(P0 >> 32), qlo = (uint32_t)P1, qhi = (uint32_t)(P1 >> 32);
+            // a lane whose only sticky state is A (whose edges the start DFA follows) has nothing to attend to; the
+            // decision is taken per WARP (one extra load per step for everybody beats a divergent branch for a few)
+            const bool needmask = __ballot_sync(__activemask(), ((plo & ~abit) | phi | qlo | qhi) != 0u) != 0u;
+            const uint32_t n = min(nv, nsteps - k);
+            uint32_t cnt = 0;
+#define RFB_QUIET_STEP(J, CHECK_N)                                                                                         \
+            {                                                                                                              \
+                if (CHECK_N && (uint32_t)(J) >= n) break;                                                                  \
+                const uint32_t w = (J) < 4 ? cur.x : (J) < 8 ? cur.y : (J) < 12 ? cur.z : cur.w;                           \
+                const uint32_t cc = (w >> (8 * ((J) & 3))) & 0xFFu;                                                        \
+                const uint32_t cls = lds16r(cmap_s + cc * 4);      /* low half of cmap[cc] */                             \
+                uint32_t t = 0;                                                                                            \
+                if (needmask) {                                                                                            \
+                    const uint32_t mrow = mask_s + cc * MSTRIDE;                                                           \
+                    if (W == 1) { const uint2 a = lds64(mrow); t = (plo & a.x) | (phi & a.y); }                            \
+                    else { const uint4 a = lds128(mrow); t = (plo & a.x) | (phi & a.y) | (qlo & a.z) | (qhi & a.w); }      \
+                    if (t != 0u && (uint32_t)((J) + 1) < n) {                                                              \
+                        /* attention: a state that dies always counts; a state that fires only if what it enters can      \
+                           outlive the NEXT symbol (look-ahead masks, image.cpp) -- most firings cannot */                 \
+                        const uint32_t wn = ((J) + 1) < 4 ? cur.x : ((J) + 1) < 8 ? cur.y : ((J) + 1) < 12 ? cur.z : cur.w; \
+                        const uint32_t cn = (wn >> (8 * (((J) + 1) & 3))) & 0xFFu;                                         \
+                        if (W == 1) {                                                                                      \
+                            const uint4 km = lds128(mrow + 16);                                                            \
+                            const uint2 lk = lds64(look_s + cn * 8);                                                       \
+                            t = (plo & ~km.x) | (phi & ~km.y) | (plo & km.z & lk.x) | (phi & km.w & lk.y);                 \
+                        } else {                                                                                           \
+                            const uint4 kk = lds128(mrow + 16), mm = lds128(mrow + 32), lk = lds128(look_s + cn * 16);     \
+                            t = (plo & ~kk.x) | (phi & ~kk.y) | (qlo & ~kk.z) | (qhi & ~kk.w) |                            \
+                                (plo & mm.x & lk.x) | (phi & mm.y & lk.y) | (qlo & mm.z & lk.z) | (qhi & mm.w & lk.w);     \
+                        }                                                                                                  \
+                    }                                                                                                      \
+                }                                                                                                          \
+                const int e = ld_dfa(d, hot_rows, hot_s, d * ncls + cls, dfa_dt);                                          \
+                if ((t | ((uint32_t)e & 0x80000000u)) != 0u) break;   /* STEP takes this symbol */                         \
+                d = (uint32_t)e;                                                                                           \
+                cnt = (uint32_t)((J) + 1);                                                                                 \
+            }
+            if (n == (uint32_t)RFB_QUIET_STEPS) {        // a whole chunk ahead: no per-step limit checks
+#pragma unroll
+                for (int J = 0; J < RFB_QUIET_STEPS; J++) RFB_QUIET_STEP(J, false)
+            } else {
+#pragma unroll
+                for (int J = 0; J < RFB_QUIET_STEPS; J++) RFB_QUIET_STEP(J, true)
+            }
+#undef RFB_QUIET_STEP
+            k += cnt; nv -= cnt;
+            evt = cnt != n;
+            if (nv && cnt) shr_bytes(cur, cnt);
+        }
+        __syncwarp();
+        // ---- STEP: one whole symbol step ----
+        if (!done && (!have || k == nsteps || (nv != 0u && (evt || rp != re)))) {
             if (have && k == nsteps) {                   // stream finished
                 if (batch.state_out)
                     lane_export_state(nfa.orig_of_id, nfa.dfa_mem_ptr, nfa.dfa_mem_ids, batch.state_out + (size_t)sid * (1u + batch.state_cap),
@@ -330,7 +350,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                         const unsigned int need = sid / batch.chunk_streams + 1u;
                         while (ld_acquire(batch.ready) < need) __nanosleep(256);
                     }
-                    P0 = 0; P1 = 0; rp = 0; re = 0; wp = 0; filt = 0; d = 0; k = 0;
+                    P0 = 0; P1 = 0; rp = 0; re = 0; d = 0; k = 0;
                     if (batch.state_in) {   // resume: the stream's active set as left by an earlier call
                         const unsigned int *stt = batch.state_in + (size_t)sid * (1u + batch.state_cap);
                         const uint32_t ns = stt[0] <= batch.state_cap ? stt[0] : 0u;   // an overflow mark cannot be resumed: treated as empty (rfb_scan rejects it)
@@ -340,10 +360,9 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                             const uint32_t id = nfa.id_of_orig[stt[1 + q]];
                             if (id == 0xFFFFFFFFu) continue;          // a state of another part
                             if (id < nsb) { if (W == 1 || id < 64) P0 |= 1ull << (id & 63); else P1 |= 1ull << (id & 63); }
-                            else if (((wp + ROW) & RMASK) == rp) fits = false;
-                            else { ring_st(lb + wp, id); wp = (wp + ROW) & RMASK; }
+                            else if (((re + ROW) & RMASK) == rp) fits = false;
+                            else { ring_st(lb + re, id); re = (re + ROW) & RMASK; }
                         }
-                        re = wp;
                         if (!fits) {   // more transient members than the ring holds: the general kernel takes the whole stream
                             const unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
                             out.rescan[slot] = make_uint2(sid, 0u);
@@ -351,129 +370,146 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                         }
                     } else if (h.start_id < nsb) {                                        // Design/FPGA.v:146-147
                         if (W == 1 || h.start_id < 64) P0 = 1ull << (h.start_id & 63); else P1 = 1ull << (h.start_id & 63);
-                    } else { ring_st(lb, h.start_id); re = ROW; wp = ROW; }
+                    } else { ring_st(lb, h.start_id); re = ROW; }
                     break;
                 }
-                if (sid >= batch.n_streams) break;       // this lane is done
-                // input: aligned 16-byte chunks; the first one is shifted down to the stream's first byte
-                const uint8_t *sp = stream_ptr(batch, sid);
-                np = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15);
-                lastc = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(sp + (nsteps - 1u)) & ~(uintptr_t)15);
-                const uint32_t off = (uint32_t)(sp - np);
-                cur = ld_in_ordered(np);
-                shr_bytes(cur, off);
-                nv = 16u - off;
-                if (np < lastc) { np += 16; pre = ld_in_ordered(np); }
-                have = true; calm = false;
-            }
-            // ---- open step k: next symbol ----
-            c = cur.x & 0xFFu;
-            cur.x = __funnelshift_r(cur.x, cur.y, 8); cur.y = __funnelshift_r(cur.y, cur.z, 8); cur.z = __funnelshift_r(cur.z, cur.w, 8); cur.w >>= 8;
-            nv--;
-            const uint32_t mrow = mask_s + c * MSTRIDE;
-            const uint4 a = lds128(mrow);               // attention masks (W == 1: | start-DFA class | symbol hash)
-            uint32_t cls;
-            if (W == 1) { cls = a.z; hf = a.w; }
-            else { const uint2 ch = lds64(mrow + CM_OFF); cls = ch.x; hf = ch.y; }
-            hc = hf & nbm;                              // a hashed row uses the low bits of the symbol hash
-            // start DFA: one lookup steps all the never-materialised successors of the always-active state A
-            {
-                d = max(d, (uint32_t)P0 & abit);
-                const uint32_t at = d * ncls + cls;
-                const int e = d < hot_rows ? lds_s16(hot_s + at * 2) : ldg_s16(dfa_dt + at);
-                d = (uint32_t)e & 0x7FFFu;
-                if (e < 0) x = __ldg(nfa.dfa_dta + at);   // sticky / accepting / untracked successors to insert
-            }
-            // sticky states: survivors P & K[c]; those in P & M[c] fire their rows
-            {
-                bool attn;
-                if (W == 1) attn = (((uint32_t)P0 & a.x) | ((uint32_t)(P0 >> 32) & a.y)) != 0;
-                else attn = (((uint32_t)P0 & a.x) | ((uint32_t)(P0 >> 32) & a.y) | ((uint32_t)P1 & a.z) | ((uint32_t)(P1 >> 32) & a.w)) != 0;
-                if (attn) {
-                    if (W == 1) {
-                        const uint4 km = lds128(mrow + 16);
-                        i0 = (uint32_t)P0 & km.z; i1 = (uint32_t)(P0 >> 32) & km.w;
-                        P0 &= (uint64_t)km.x | ((uint64_t)km.y << 32);
-                    } else {
-                        const uint4 kk = lds128(mrow + 16);
-                        const uint4 mm = lds128(mrow + 32);
-                        i0 = (uint32_t)P0 & mm.x; i1 = (uint32_t)(P0 >> 32) & mm.y;
-                        i2 = (uint32_t)P1 & mm.z; i3 = (uint32_t)(P1 >> 32) & mm.w;
-                        P0 &= (uint64_t)kk.x | ((uint64_t)kk.y << 32);
-                        P1 &= (uint64_t)kk.z | ((uint64_t)kk.w << 32);
-                    }
-                    firing = (i0 | i1 | i2 | i3) != 0;
+                if (sid >= batch.n_streams) done = true;   // this lane is done
+                else {
+                    // input: aligned 16-byte chunks; the first one is shifted down to the stream's first byte
+                    const uint8_t *sp = stream_ptr(batch, sid);
+                    np = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(sp) & ~(uintptr_t)15);
+                    const uint32_t off = (uint32_t)(sp - np);
+                    cur = ld_in_ordered(np);
+                    shr_bytes(cur, off);
+                    nv = 16u - off;
+                    if (nsteps > nv) { np += 16; pre = ld_in_ordered(np); }
+                    have = true;
                 }
             }
-            pend = x != NONE || rp != re || firing;
-            calm = !pend;
-            if (!pend) RFB_CLOSE_STEP();
-        }
-        // ---- DRAIN: one work item of the open step ----
-        if (pend) {
-            bool hit = false, look = walking;
-            uint32_t t = 0;
-            if (!walking) {
-                if (x != NONE) {                                  // entry of a start-DFA insertion list: the target itself
-                    hit = true;
-                    const uint32_t tl = __ldg(nfa.dfa_act + x);
-                    t = tl & 0x7FFFu;
-                    x = (tl & 0x8000u) ? x + 1 : NONE;
-                } else if (rp != re) {                            // a member of S_k
-                    const uint32_t u = ring_ld(lb + rp);
-                    rp = (rp + ROW) & RMASK;
-                    idx = u + (u >= gbase ? hc : 0u);
-                    look = true;
-                    if (u - acc_base < n_acc) {                   // accepting (Design/FPGA.v:210-226)
-                        emit_match_cold(out, sid + batch.stream_id_base, k + batch.pos_base, nfa.orig_of_id[u]);
-                        look = false;
-                    }
-                } else {                                          // row of a firing sticky state
-                    uint32_t wsel, wbase;
-                    if (i0) { wsel = i0; wbase = 0; i0 &= i0 - 1; }
-                    else if (i1) { wsel = i1; wbase = 32; i1 &= i1 - 1; }
-                    else if (i2) { wsel = i2; wbase = 64; i2 &= i2 - 1; }
-                    else { wsel = i3; wbase = 96; i3 &= i3 - 1; }
-                    firing = (i0 | i1 | i2 | i3) != 0;
-                    const uint32_t sd = lds32(sdesc_s + (wbase + (uint32_t)__ffs((int)wsel) - 1u) * 4);
-                    idx = (sd & 0xFFFFu) + (hf & (sd >> 16));
-                    look = true;
+            if (!done) {
+                // ---- open step k: next symbol ----
+                const uint32_t c = cur.x & 0xFFu;
+                cur.x = __funnelshift_r(cur.x, cur.y, 8); cur.y = __funnelshift_r(cur.y, cur.z, 8); cur.z = __funnelshift_r(cur.z, cur.w, 8); cur.w >>= 8;
+                nv--;
+                const uint32_t mrow = mask_s + c * MSTRIDE;
+                const uint4 a = lds128(mrow);           // attention masks (W == 1: | start-DFA class | symbol hash)
+                uint32_t cls, hf;
+                if (W == 1) { cls = a.z; hf = a.w; }
+                else { const uint2 ch = lds64(mrow + CM_OFF); cls = ch.x; hf = ch.y; }
+                const uint32_t hc = hf & nbm;           // a hashed row uses the low bits of the symbol hash
+                uint32_t x = NONE;                      // next entry of a pending start-DFA insertion list
+                // start DFA: one lookup steps all the never-materialised successors of the always-active state A
+                {
+                    d = max(d, (uint32_t)P0 & abit);
+                    const uint32_t at = d * ncls + cls;
+                    const int e = ld_dfa(d, hot_rows, hot_s, at, dfa_dt);
+                    d = (uint32_t)e & 0x7FFFu;
+                    if (e < 0) x = __ldg(nfa.dfa_dta + at);   // sticky / accepting / untracked successors to insert
                 }
-            }
-            if (look) {
-                const uint32_t e = lds32(tab_s + idx * 4);
-                const uint32_t a = e & 0xFFu, b = (e >> 8) & 0xFFu;
-                t = (e >> 16) & 0x7FFFu;
-                walking = (e & TAB_MORE) != 0;
-                idx++;
-                if (a <= b) hit = (c == a) | (c == b);
-                else if (a == 0xFFu) { idx = t; walking = true; }                     // indirect -> chain
-                else hit = (lds32(memb_s + (((0xFEu - a) * 253u + b) * 8 + (c >> 5)) * 4) >> (c & 31)) & 1u;
-            }
-            if (hit && !ovf) {   // ---- the one insertion site: add t to S_{k+1} ----
-                if (t < nsb) {                                    // entering a sticky state
-                    const uint64_t sb = 1ull << (t & 63);
-                    // P is read only when a step opens (survivors, firing bits) and insertions happen after that:
-                    // a state entered now is first seen by the next step, as it must be
-                    if (W == 1 || t < 64) P0 |= sb; else P1 |= sb;
-                } else {
-                    const uint32_t fb = 1u << (t & 31);
-                    if (!((filt & fb) && ring_contains(lb, re, wp, ROW, RMASK, t))) {
-                        const uint32_t nw = (wp + ROW) & RMASK;
-                        if (nw == rp) ovf = true;                 // ring full: hand the stream to the general kernel
-                        else {
-                            ring_st(lb + wp, t);
-                            wp = nw;
-                            filt |= fb;
+                // sticky states: survivors P & K[c]; those in P & M[c] fire their rows
+                uint32_t i0 = 0, i1 = 0, i2 = 0, i3 = 0;  // firing sticky bits not yet expanded
+                {
+                    bool attn;
+                    if (W == 1) attn = (((uint32_t)P0 & a.x) | ((uint32_t)(P0 >> 32) & a.y)) != 0;
+                    else attn = (((uint32_t)P0 & a.x) | ((uint32_t)(P0 >> 32) & a.y) | ((uint32_t)P1 & a.z) | ((uint32_t)(P1 >> 32) & a.w)) != 0;
+                    if (attn) {
+                        if (W == 1) {
+                            const uint4 km = lds128(mrow + 16);
+                            i0 = (uint32_t)P0 & km.z; i1 = (uint32_t)(P0 >> 32) & km.w;
+                            P0 &= (uint64_t)km.x | ((uint64_t)km.y << 32);
+                        } else {
+                            const uint4 kk = lds128(mrow + 16);
+                            const uint4 mm = lds128(mrow + 32);
+                            i0 = (uint32_t)P0 & mm.x; i1 = (uint32_t)(P0 >> 32) & mm.y;
+                            i2 = (uint32_t)P1 & mm.z; i3 = (uint32_t)(P1 >> 32) & mm.w;
+                            P0 &= (uint64_t)kk.x | ((uint64_t)kk.y << 32);
+                            P1 &= (uint64_t)kk.z | ((uint64_t)kk.w << 32);
+                        }
+                        if (nv != 0u && k + 1u < nsteps) {   // look-ahead: skip firings whose targets cannot outlive the next symbol
+                            const uint32_t cn = cur.x & 0xFFu;
+                            if (W == 1) { const uint2 lk = lds64(look_s + cn * 8); i0 &= lk.x; i1 &= lk.y; }
+                            else { const uint4 lk = lds128(look_s + cn * 16); i0 &= lk.x; i1 &= lk.y; i2 &= lk.z; i3 &= lk.w; }
                         }
                     }
                 }
+                // ---- drain every work item of the step ----
+                uint32_t wp = re;                       // next write: S_{k+1} grows behind S_k
+                uint32_t filt = 0;                      // 32-bit membership filter of this step's new entries
+                uint32_t idx = 0;
+                bool walking = false, ovf = false;
+                for (;;) {
+                    bool hit = false, look = walking;
+                    uint32_t t = 0;
+                    if (!walking) {
+                        if (x != NONE) {                                  // entry of a start-DFA insertion list: the target itself
+                            hit = true;
+                            const uint32_t tl = __ldg(nfa.dfa_act + x);
+                            t = tl & 0x7FFFu;
+                            x = (tl & 0x8000u) ? x + 1 : NONE;
+                        } else if (rp != re) {                            // a member of S_k
+                            const uint32_t u = ring_ld(lb + rp);
+                            rp = (rp + ROW) & RMASK;
+                            idx = u + (u >= gbase ? hc : 0u);
+                            look = true;
+                            if (u - acc_base < n_acc) {                   // accepting (Design/FPGA.v:210-226)
+                                emit_match_cold(out, sid + batch.stream_id_base, k + batch.pos_base, nfa.orig_of_id[u]);
+                                look = false;
+                            }
+                        } else if ((i0 | i1 | i2 | i3) != 0u) {          // row of a firing sticky state
+                            uint32_t wsel, wbase;
+                            if (i0) { wsel = i0; wbase = 0; i0 &= i0 - 1; }
+                            else if (i1) { wsel = i1; wbase = 32; i1 &= i1 - 1; }
+                            else if (i2) { wsel = i2; wbase = 64; i2 &= i2 - 1; }
+                            else { wsel = i3; wbase = 96; i3 &= i3 - 1; }
+                            const uint32_t sd = lds32(sdesc_s + (wbase + (uint32_t)__ffs((int)wsel) - 1u) * 4);
+                            idx = (sd & 0xFFFFu) + (hf & (sd >> 16));
+                            look = true;
+                        } else break;                                     // the step is drained
+                    }
+                    if (look) {
+                        const uint32_t e = lds32(tab_s + idx * 4);
+                        const uint32_t ea = e & 0xFFu, eb = (e >> 8) & 0xFFu;
+                        t = (e >> 16) & 0x7FFFu;
+                        walking = (e & TAB_MORE) != 0;
+                        idx++;
+                        if (ea <= eb) hit = (c == ea) | (c == eb);
+                        else if (ea == 0xFFu) { idx = t; walking = true; }                     // indirect -> chain
+                        else hit = (lds32(memb_s + (((0xFEu - ea) * 253u + eb) * 8 + (c >> 5)) * 4) >> (c & 31)) & 1u;
+                    }
+                    if (hit && !ovf) {   // ---- the one insertion site: add t to S_{k+1} ----
+                        if (t < nsb) {                                    // entering a sticky state
+                            const uint64_t sb = 1ull << (t & 63);
+                            // P was read when the step opened (survivors, firing bits) and insertions happen after that:
+                            // a state entered now is first seen by the next step, as it must be
+                            if (W == 1 || t < 64) P0 |= sb; else P1 |= sb;
+                        } else {
+                            const uint32_t fb = 1u << (t & 31);
+                            if (!((filt & fb) && ring_contains(lb, re, wp, ROW, RMASK, t))) {
+                                const uint32_t nw = (wp + ROW) & RMASK;
+                                if (nw == rp) ovf = true;                 // ring full: hand the stream to the general kernel
+                                else {
+                                    ring_st(lb + wp, t);
+                                    wp = nw;
+                                    filt |= fb;
+                                }
+                            }
+                        }
+                    }
+                }
+                // ---- close: current <= next (Design/FPGA.v:733-737); rp == re: S_k is consumed ----
+                re = wp; k++; evt = false;
+                if (ovf) {   // a full ring hands the stream to the general kernel: S_{k-1} was fully examined, that kernel
+                             // re-runs the stream and reports from step k on (after the last step there is nothing left to
+                             // report, but the caller may want S_{n_steps}: only that kernel has it)
+                    if (k < nsteps || batch.state_out) {
+                        const unsigned int slot_ = atomicAdd(&out.g->n_rescan, 1u);
+                        out.rescan[slot_] = make_uint2(sid, k);
+                    }
+                    have = false;
+                }
             }
-            pend = walking || x != NONE || rp != re || firing;
-            if (!pend) RFB_CLOSE_STEP();
         }
     }
-#undef RFB_CLOSE_STEP
 }
 
 cudaError_t launch_scan_lane(const NfaDev &nfa_in, const BatchDev &batch, const OutDev &out, int n_sms, cudaStream_t stream) {

@@ -63,6 +63,10 @@ int main(int argc, char **argv) {
             bool attn = false;
             for (uint32_t w = 0; w < W; w++) attn |= (P[w] & A[w]) != 0;
             if (attn) for (uint32_t w = 0; w < W; w++) { fire[w] = P[w] & M[w]; P[w] &= K[w]; }
+            if (attn && k + 1 < n_steps) {   // look-ahead: a firing whose targets cannot outlive the next symbol is skipped
+                const uint64_t *LK = (const uint64_t *)&img.blob[h.off_look + sp[k + 1] * 8 * W];
+                for (uint32_t w = 0; w < W; w++) fire[w] &= LK[w];
+            }
             // drain
             for (uint32_t t : pending) insert(t);
             for (uint32_t u : cur) {

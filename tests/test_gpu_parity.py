@@ -621,3 +621,39 @@ def test_image_file_save_load_scan(gpu_ctx, snort, tmp_path):
     assert recs_tuple(a.records) == recs_tuple(b.records) and a.n_matches == 3 * nfa.scan(data[:32], 32, n_steps=1500, stride=1536).n_matches
     with pytest.raises(R.RfbError):
         gpu_ctx.load_image(tmp_path / "missing.rfbimg")
+
+
+@pytest.mark.parametrize("name", ["snort_16", "l7_filter"])
+def test_calibration_changes_no_result(gpu_ctx, snort, l7, name):
+    """rfb_nfa_calibrate renumbers the start-DFA states by measured visit frequency (device tables only): records,
+    counts and exported final sets must be what they were before, and still equal the oracle's."""
+    rs = snort if name == "snort_16" else l7
+    nfa = gpu_ctx.nfa_from_entries(rs.entries)
+    n, L = 1024, 777
+    data = WL.make_batch_numpy("wmix", rs.lo, rs.hi, n, L, 800, seed=0x5EED0300)
+    assert nfa.calibration()[0] is False
+    before = nfa.scan(data, n, n_steps=L, stride=800, want_state=True, state_cap=127)
+    sample = WL.make_batch_numpy("whi", rs.lo, rs.hi, 256, 1500, 1536, seed=0x5EED0301)
+    nfa.calibrate(sample, 256, 1500, 1536)
+    done, symbols, hot = nfa.calibration()
+    assert done and symbols == 256 * 1499 and 0.0 < hot <= 1.0
+    after = nfa.scan(data, n, n_steps=L, stride=800, want_state=True, state_cap=127)
+    assert recs_tuple(after.records) == recs_tuple(before.records) and np.array_equal(after.counts, before.counts)
+    for s in range(n):
+        assert sorted(after.state[s, 1: 1 + after.state[s, 0]].tolist()) == sorted(before.state[s, 1: 1 + before.state[s, 0]].tolist())
+    want = O.b_scan_many(rs.entries, rs.n_states, data, n, 800, L)
+    assert recs_tuple(after.records) == recs_tuple(want["recs"]) and np.array_equal(after.counts, want["counts"])
+    # calibrating again on other traffic is allowed at any time
+    nfa.calibrate(WL.make_batch_numpy("uniform", None, None, 64, 1500, 1536), 64, 1500, 1536)
+    again = nfa.scan(data, n, n_steps=L, stride=800)
+    assert recs_tuple(again.records) == recs_tuple(want["recs"])
+
+
+def test_auto_calibration_on_the_first_large_batch(gpu_ctx, snort):
+    nfa = gpu_ctx.nfa_from_entries(snort.entries)
+    n = 8192
+    data = WL.make_batch_numpy("wmix", snort.lo, snort.hi, n, 300, 320, seed=0x5EED0302)
+    got = nfa.scan(data, n, n_steps=300, stride=320)
+    assert nfa.calibration()[0] is True
+    want = O.b_scan_many(snort.entries, snort.n_states, data, n, 320, 300)
+    assert recs_tuple(got.records) == recs_tuple(want["recs"]) and np.array_equal(got.counts, want["counts"])

@@ -31,7 +31,7 @@ def test_round_trip_shipped_rulesets(snort, l7, tmp_path):
         info = R.image_file_check(p)
         assert info == R.image_check(rs.entries)            # same tables as a fresh build
         raw = p.read_bytes()
-        assert raw[:8] == b"RFBIMG\x00\x01" and struct.unpack_from("<II", raw, 8) == (1, 1)
+        assert raw[:8] == b"RFBIMG\x00\x01" and struct.unpack_from("<II", raw, 8) == (2, 1)
         n_entries, n_states = struct.unpack_from("<QI", raw, 16)
         assert n_states == rs.n_states and n_entries == rs.entries.size
         assert np.array_equal(np.frombuffer(raw, np.uint32, n_entries, 32), rs.entries)   # the .coe contents, verbatim
@@ -98,3 +98,45 @@ def test_random_nfas_round_trip(tmp_path):
         p = tmp_path / f"r{k}.rfbimg"
         R.image_file_build(E, p, n)
         assert R.image_file_check(p) == R.image_check(E, n)
+
+
+def test_aliased_state_ids_are_refused(l7, tmp_path):
+    """A resealed file in which a second table slot names an existing state (orig_of_id[alias] = s) and an edge is
+    re-pointed at the alias: the per-(state, symbol) proof maps ids back through orig_of_id and would still see the
+    right successor, while the kernel would follow the alias's arbitrary row.  The structural check demands that
+    orig_of_id be the exact inverse of id_of_orig."""
+    p = tmp_path / "a.rfbimg"
+    R.image_file_build(l7.entries, p)
+    raw = bytearray(p.read_bytes())
+    n_entries = struct.unpack_from("<Q", raw, 16)[0]
+    at = 32 + 4 * n_entries
+    n_group, image_ok, header_bytes = struct.unpack_from("<III", raw, at)
+    assert n_group == 0 and image_ok == 1
+    at += 12
+    hdr = struct.unpack_from("<%dI" % (header_bytes // 4), raw, at)
+    n_slots, off_tab = hdr[0], hdr[12]
+    at += header_bytes
+    n_blob = struct.unpack_from("<Q", raw, at)[0]
+    blob_at = at + 8
+    at = blob_at + n_blob
+    n_orig = struct.unpack_from("<Q", raw, at)[0]
+    orig_at = at + 8
+    assert n_orig == n_slots
+    orig = np.frombuffer(bytes(raw[orig_at:orig_at + 4 * n_orig]), np.uint32).copy()
+    tab = np.frombuffer(bytes(raw[blob_at + off_tab:blob_at + off_tab + 4 * n_slots]), np.uint32).copy()
+    free = [i for i in range(n_slots - 1, 0, -1) if orig[i] == 0xFFFFFFFF]
+    assert free, "the image has no unused slot to alias"
+    alias = free[0]
+    # an ordinary single-target record whose target is a real state
+    victim = next(i for i in range(n_slots) if (tab[i] & 0xFF) <= ((tab[i] >> 8) & 0xFF) and orig[(tab[i] >> 16) & 0x7FFF] != 0xFFFFFFFF
+                  and orig[i] != 0xFFFFFFFF and ((tab[i] >> 16) & 0x7FFF) >= 128)
+    target = (int(tab[victim]) >> 16) & 0x7FFF
+    tab[victim] = (int(tab[victim]) & 0x8000FFFF) | (alias << 16)
+    orig[alias] = orig[target]
+    raw[blob_at + off_tab:blob_at + off_tab + 4 * n_slots] = tab.tobytes()
+    raw[orig_at:orig_at + 4 * n_orig] = orig.tobytes()
+    q = tmp_path / "alias.rfbimg"
+    q.write_bytes(reseal(raw))
+    with pytest.raises(R.RfbError) as e:
+        R.image_file_check(q)
+    assert "inverse" in str(e.value)

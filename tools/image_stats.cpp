@@ -20,7 +20,7 @@ static uint64_t splitmix64(uint64_t x) {
     return z ^ (z >> 31);
 }
 
-struct Stats { double t2hits = 0, entries = 0, lookups = 0, indirect = 0, cls = 0, pushes = 0, attn = 0, inj = 0, sticky = 0, symbols = 0, maxlist = 0; };
+struct Stats { double surv = 0, inj_useful = 0, t2hits = 0, entries = 0, lookups = 0, indirect = 0, cls = 0, pushes = 0, attn = 0, inj = 0, sticky = 0, symbols = 0, maxlist = 0; };
 
 int main(int argc, char **argv) {
     if (argc < 4) return 1;
@@ -55,7 +55,25 @@ int main(int argc, char **argv) {
             uint64_t Pn[2] = {0, 0};
             std::set<uint32_t> seen;
             uint32_t lk = 0;   // loop iterations of this lane in this step (pops of accept states count too)
-            auto push = [&](uint32_t t) { s.pushes++; if (t < h.nsb) Pn[t >> 6] |= 1ull << (t & 63); else if (seen.insert(t).second) nxt.push_back(t); };
+            const uint32_t cnext = k + 1 < L ? src[off + k + 1] : 0x100u;
+            // would target t have any effect beyond this step? (sticky / accepting / has an edge on the NEXT symbol)
+            auto survives = [&](uint32_t t) -> bool {
+                if (cnext > 0xFF) return true;
+                if (t < h.nsb || t - h.acc_base < h.n_acc) return true;
+                const uint32_t hf2 = ((cnext * h.hash_mul) >> h.hash_shift) & 0xFF, hc2 = hf2 & ((1u << h.bucket_bits) - 1);
+                uint32_t idx = t + (t >= h.gbase ? hc2 : 0);
+                for (;;) {
+                    uint32_t e = tab[idx], a = e & 0xFF, b = (e >> 8) & 0xFF, tt = (e >> 16) & 0x7FFF;
+                    if (a <= b) { if (cnext == a || cnext == b) return true; }
+                    else if (a == 0xFF) { idx = tt; continue; }
+                    else { uint32_t n = (0xFE - a) * 253 + b; if ((memb[n * 8 + (cnext >> 5)] >> (cnext & 31)) & 1) return true; }
+                    if (!(e & TAB_MORE)) break;
+                    idx++;
+                }
+                return false;
+            };
+            bool any_surv = false;
+            auto push = [&](uint32_t t) { s.pushes++; if (survives(t)) { s.surv++; any_surv = true; } if (t < h.nsb) Pn[t >> 6] |= 1ull << (t & 63); else if (seen.insert(t).second) nxt.push_back(t); };
             auto walk = [&](uint32_t idx) {
                 for (;;) {
                     uint32_t e = tab[idx]; lk++;
@@ -83,13 +101,19 @@ int main(int argc, char **argv) {
             bool attn = false;
             uint64_t im[2] = {0, 0};
             for (uint32_t w = 0; w < W; w++) { attn |= (P[w] & A[w]) != 0; s.sticky += __builtin_popcountll(P[w]); }
-            if (attn) { s.attn++; for (uint32_t w = 0; w < W; w++) { im[w] = P[w] & M[w]; P[w] &= K[w]; } }
+            if (attn) {
+                bool real = false;
+                for (uint32_t w = 0; w < W; w++) { im[w] = P[w] & M[w]; if (P[w] & ~K[w]) real = true; P[w] &= K[w]; }
+                if (k + 1 < L && !getenv("NO_LOOKAHEAD")) { const uint64_t *LK = (const uint64_t *)&img.blob[h.off_look + src[off + k + 1] * 8 * W]; for (uint32_t w = 0; w < W; w++) im[w] &= LK[w]; }
+                for (uint32_t w = 0; w < W; w++) if (im[w]) real = true;
+                if (real) s.attn++;
+            }
             for (uint32_t u : cur) {
                 if (u - h.acc_base < h.n_acc) { lk++; continue; }
                 walk(u + (u >= h.gbase ? hc : 0));
             }
             for (uint32_t w = 0; w < W; w++)
-                while (im[w]) { uint32_t b = __builtin_ctzll(im[w]) + 64 * w; im[w] &= im[w] - 1; s.inj++; walk((sdesc[b] & 0xFFFF) + (hf & (sdesc[b] >> 16))); }
+                while (im[w]) { uint32_t b = __builtin_ctzll(im[w]) + 64 * w; im[w] &= im[w] - 1; s.inj++; any_surv = false; walk((sdesc[b] & 0xFFFF) + (hf & (sdesc[b] >> 16))); if (any_surv) s.inj_useful++; }
             s.lookups += lk; per_sym_lookups[j][k] = lk;
             for (uint32_t w = 0; w < W; w++) P[w] |= Pn[w];
             cur.swap(nxt); nxt.clear(); s.symbols++;
@@ -123,6 +147,7 @@ int main(int argc, char **argv) {
     }
     for (int t = 0; t < 2; t++) {
         Stats &s = st[t];
+        printf("%s: per symbol: pushes surviving the next symbol %.4f of %.4f; firings with a surviving target %.4f of %.4f\n", t ? "hi" : "lo", s.surv / s.symbols, s.pushes / s.symbols, s.inj_useful / s.symbols, s.inj / s.symbols);
         printf("%s: per symbol: t2hits %.3f entries %.3f lookups %.3f indirect %.3f class %.3f pushes %.3f attn %.3f inj %.3f sticky %.2f maxlist %.0f\n", t ? "hi" : "lo", s.t2hits / s.symbols,
                s.entries / s.symbols, s.lookups / s.symbols, s.indirect / s.symbols, s.cls / s.symbols, s.pushes / s.symbols, s.attn / s.symbols, s.inj / s.symbols, s.sticky / s.symbols, s.maxlist);
     }
