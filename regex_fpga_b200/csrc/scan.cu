@@ -198,6 +198,9 @@ __device__ __forceinline__ int lds_s16(uint32_t a) { int v; asm("ld.shared.s16 %
 #ifndef RFB_QUIET_STEPS
 #define RFB_QUIET_STEPS 16   // symbols per quiet run (<= 16: one input chunk)
 #endif
+#ifndef RFB_STEP_REPS
+#define RFB_STEP_REPS 2      // general steps a busy stream may take per iteration (measured: 1 / 2 / 4 / 8, profiles/README.md)
+#endif
 
 // v >>= 8 * nb (nb in 0..15), branch-free
 __device__ __forceinline__ void shr_bytes(uint4 &v, uint32_t nb) {
@@ -262,16 +265,25 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     bool have = false;
     bool evt = false;                                   // the quiet run stopped in front of an event: STEP takes that symbol
     bool done = false;                                  // no stream left for this lane
+#ifdef RFB_STATS
+    unsigned long long st_iter = 0, st_qruns = 0, st_qsteps = 0, st_qzero = 0, st_steps = 0, st_items = 0, st_qfast = 0;
+#define RFB_STAT(x) x
+#else
+#define RFB_STAT(x)
+#endif
 
     for (;;) {
         // All 32 lanes stay in the loop until the last one is done, and meet here once per iteration: both blocks are
         // entered by converged lanes (a lane that leaves a block early waits for the others at the next meeting point
         // instead of running ahead through private copies of the code).
         if (__all_sync(0xffffffffu, done)) break;
-        if (have && nv == 0u) {                          // next chunk
-            cur = pre; nv = 16u;
-            if (nsteps - k > 16u) { np += 16; pre = ld_in(np); }     // the stream goes on behind it
-        }
+        RFB_STAT(if (!done) st_iter++;)
+#define RFB_NEXT_CHUNK()                                                                        \
+        do {                                                                                     \
+            cur = pre; nv = 16u;                                                                 \
+            if (nsteps - k > 16u) { np += 16; pre = ld_in(np); }   /* the stream goes on behind it */ \
+        } while (0)
+        if (have && nv == 0u) RFB_NEXT_CHUNK();
         // ---- QUIET run: to the end of the bytes at hand, or to the first symbol with an event ----
         if (have && !evt && rp == re && nv != 0u && k < nsteps) {
             d = max(d, (uint32_t)P0 & abit);             // A entered the set (it never leaves): 0 -> 1
@@ -313,7 +325,9 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                 d = (uint32_t)e;                                                                                           \
                 cnt = (uint32_t)((J) + 1);                                                                                 \
             }
-            if (n == (uint32_t)RFB_QUIET_STEPS) {        // a whole chunk ahead: no per-step limit checks
+            // one version of the run for the whole warp: without per-step limit checks only if EVERY lane in the run has a
+            // whole chunk ahead (two versions side by side would run one after the other)
+            if (__all_sync(__activemask(), n == (uint32_t)RFB_QUIET_STEPS)) {
 #pragma unroll
                 for (int J = 0; J < RFB_QUIET_STEPS; J++) RFB_QUIET_STEP(J, false)
             } else {
@@ -322,6 +336,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             }
 #undef RFB_QUIET_STEP
             k += cnt; nv -= cnt;
+            RFB_STAT(st_qruns++; st_qsteps += cnt; st_qzero += cnt == 0; st_qfast += n == 16u;)
             evt = cnt != n;
             if (nv && cnt) shr_bytes(cur, cnt);
         }
@@ -386,8 +401,16 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     have = true;
                 }
             }
-            if (!done) {
+            // a stream whose transient set stays non-empty takes its next symbols here as well (up to RFB_STEP_REPS per
+            // iteration): busy streams then need fewer iterations, each of which also pays for a quiet block
+#pragma unroll 1
+            for (int rep = 0; !done && rep < RFB_STEP_REPS; rep++) {
+                if (rep != 0) {
+                    if (!(have && k != nsteps && rp != re)) break;
+                    if (nv == 0u) RFB_NEXT_CHUNK();
+                }
                 // ---- open step k: next symbol ----
+                RFB_STAT(st_steps++;)
                 const uint32_t c = cur.x & 0xFFu;
                 cur.x = __funnelshift_r(cur.x, cur.y, 8); cur.y = __funnelshift_r(cur.y, cur.z, 8); cur.z = __funnelshift_r(cur.z, cur.w, 8); cur.w >>= 8;
                 nv--;
@@ -466,6 +489,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                             look = true;
                         } else break;                                     // the step is drained
                     }
+                    RFB_STAT(st_items++;)
                     if (look) {
                         const uint32_t e = lds32(tab_s + idx * 4);
                         const uint32_t ea = e & 0xFFu, eb = (e >> 8) & 0xFFu;
@@ -510,6 +534,15 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             }
         }
     }
+#ifdef RFB_STATS
+    if (out.counts) {   // dev build only: loop statistics land in the LAST seven counters of the count vector
+        unsigned long long *cs = out.counts + (nfa.n_ref_states - 7);
+        atomicAdd(cs + 0, st_iter); atomicAdd(cs + 1, st_qruns); atomicAdd(cs + 2, st_qsteps); atomicAdd(cs + 3, st_qzero);
+        atomicAdd(cs + 4, st_steps); atomicAdd(cs + 5, st_items); atomicAdd(cs + 6, st_qfast);
+    }
+#endif
+#undef RFB_STAT
+#undef RFB_NEXT_CHUNK
 }
 
 cudaError_t launch_scan_lane(const NfaDev &nfa_in, const BatchDev &batch, const OutDev &out, int n_sms, cudaStream_t stream) {
