@@ -48,15 +48,13 @@ def load_ruleset(name="snort_16"):
     return z["entries"], int(z["n_states"]), z["lo"], z["hi"]
 
 
-def measured_traffic(sym_per_launch):
-    """DRAM bytes per launch of the lane kernel from the committed ncu capture (profiles/r1_traffic.json), scaled by
-    the symbols one launch processes; None when the capture is absent."""
-    p = os.path.join(ROOT, "profiles", "r1_traffic.json")
+def ncu_capture():
+    """Per-symbol figures of the lane kernel from the committed ncu capture of the shipped build on this workload
+    (profiles/r2_kernel.json: DRAM bytes and warp instructions per symbol); {} when absent."""
     try:
-        t = json.load(open(p))
-        return int(round(t["dram_bytes_per_symbol"] * sym_per_launch))
+        return json.load(open(os.path.join(ROOT, "profiles", "r2_kernel.json")))
     except Exception:
-        return None
+        return {}
 
 
 def measured_peaks():
@@ -130,14 +128,35 @@ def cpu_sample(E, n_states, lo, hi, mix, n_pairs, first_stream=0):
     return WL.make_batch_numpy(mix, lo, hi, 2 * n_pairs, STREAM_LEN, STRIDE, SEED, first_stream)
 
 
+def cpu_reference_kind():
+    """"reference": oracle/_ref/libref.so -- the reference's OWN Design/FPGA.v translated to C (oracle/vsim) and clocked
+    like its testbench; built in the build container from /root/reference and shipped prebuilt to the GPU box.
+    "port": the hand-written cycle-level restatement (oracle/oracle_a.c), only if that library is missing."""
+    from oracle import ref_py as RF
+    try:
+        RF.lib()
+        return "reference"
+    except Exception:
+        return "port"
+
+
 def run_cpu_reference(E, n_states, sample, n_pairs, threads):
-    """Cycle-level oracle (FPGA.v + ROM + testbench), one (lo,hi) stream pair per thread at a time.
+    """The reference design (FPGA.v + ROM + testbench) on host threads, one (lo,hi) stream pair per thread at a time.
     TB semantics: an M-entry trace pair yields 2*(M-1) symbol steps."""
-    from oracle import oracle_py as O
     t0 = time.perf_counter()
-    r = O.a_run_many(E, n_states, sample, n_pairs, STRIDE, STREAM_LEN, n_threads=threads, fast_idle=False)
+    if cpu_reference_kind() == "reference":
+        from oracle import ref_py as RF
+        r = RF.tb_run_many(E, n_states, sample, n_pairs, STRIDE, STREAM_LEN, n_threads=threads)
+    else:
+        from oracle import oracle_py as O
+        r = O.a_run_many(E, n_states, sample, n_pairs, STRIDE, STREAM_LEN, n_threads=threads, fast_idle=False)
     dt = time.perf_counter() - t0
     return r["symbols"], r["cycles"], dt
+
+
+CPU_NOTE = {"reference": "the reference's own Design/FPGA.v executed on the host: translated to C by oracle/vsim/v2c.py and clocked as "
+                         "Simulation/testbench_BLK_Mem.sv clocks it (oracle/_ref/libref.so), one (lo,hi) pair per thread",
+            "port": "cycle-level C restatement of Design/FPGA.v + testbench (oracle/oracle_a.c): oracle/_ref/libref.so is missing here"}
 
 
 def reference_arm(args, rank, world):
@@ -162,10 +181,8 @@ def reference_arm(args, rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total / max(1, args.steps) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": gbit, "unit": "Gbit/s", "cores": threads, "kind": "port", "sample": desc,
-                         "simulated_cycles_per_s": cycles / total,
-                         "note": "cycle-level C restatement of Design/FPGA.v + testbench (oracle/oracle_a.c); "
-                                 "the Verilog cannot be simulated here (no Verilator/Icarus in the image)"},
+        "cpu_baseline": {"value": gbit, "unit": "Gbit/s", "cores": threads, "kind": cpu_reference_kind(), "sample": desc,
+                         "simulated_cycles_per_s": cycles / total, "note": CPU_NOTE[cpu_reference_kind()]},
         "e2e": {"value": gbit, "unit": "Gbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -224,6 +241,70 @@ def run_e2e(args, torch, dist, nfa, batch, n, first, cap, n_states, n_matches, b
     assert out.n_matches == n_matches, "host-pointer and device-pointer scans disagree"
     return {"value": world * sym_per_step * 8 / e2e_s / 1e9, "unit": "Gbit/s", "h2d_bytes_per_step": int(host_np.size),
             "d2h_bytes_per_step": int(n_states * 8 + out.n_records * 12 + 32), "steps": e2e_steps, "s_per_step": e2e_s}
+
+
+# ------------------------------------------------------------------------------------------------
+# parity of the measured run (outside every timed region)
+# ------------------------------------------------------------------------------------------------
+PARITY_SAMPLE = 1024
+
+
+def check_parity(torch, dist, shard, E, n_states, batch, n, first, world, rank, dev, counts, recs, n_records, n_dropped):
+    """What the last pass of THIS run computed, against the CPU oracle, at every N (outside the timed regions):
+      * records of a strided sample of PARITY_SAMPLE global stream ids spanning every shard: each rank copies its
+        sampled streams back from its device batch, scans them with oracle B, and compares with the records the GPU
+        wrote for exactly those streams (global ids via stream_id_base); shard.gather_records then brings both sides
+        to every rank and rank 0 compares the concatenations (the gather path);
+      * on every rank the per-state counts equal the histogram of its own records (counts and records are the same
+        pulses), and the NCCL all-reduce of the count vectors equals the sum of the all-gathered per-rank vectors.
+    Raises (the run fails) on any mismatch."""
+    from oracle import oracle_py as O
+    from regex_fpga_b200.engine import MATCH_DTYPE
+    total = n * world
+    sample = np.unique((np.arange(PARITY_SAMPLE, dtype=np.int64) * total) // PARITY_SAMPLE)
+    mine = sample[(sample >= first) & (sample < first + n)]
+    rec = recs[: 3 * n_records].view(-1, 3)
+    hist = torch.zeros(n_states, dtype=torch.int64, device=dev)
+    if n_records:
+        hist.index_add_(0, rec[:, 2].long(), torch.ones(n_records, dtype=torch.int64, device=dev))
+    counts_vs_records = bool(torch.equal(counts, hist)) and n_dropped == 0
+    reduce_ok = None
+    if dist is not None:
+        red = counts.clone()
+        shard.reduce_counts(red, dist)
+        parts = [torch.zeros_like(counts) for _ in range(world)]
+        dist.all_gather(parts, counts)
+        reduce_ok = bool(torch.equal(red, torch.stack(parts).sum(0)))
+    # GPU records of the sampled streams
+    sel = torch.isin(rec[:, 0].long(), torch.from_numpy(mine).to(dev)) if n_records else torch.zeros(0, dtype=torch.bool, device=dev)
+    g = rec[sel].cpu().numpy().astype(np.uint32).reshape(-1, 3)
+    g = g[np.lexsort((g[:, 2], g[:, 1], g[:, 0]))]
+    got = np.zeros(g.shape[0], dtype=MATCH_DTYPE)
+    got["stream"], got["pos"], got["state"] = g[:, 0], g[:, 1], g[:, 2]
+    # oracle on the same bytes
+    local = torch.from_numpy(mine - first).to(dev)
+    data = batch[local].cpu().numpy()
+    w = O.b_scan_many(E, n_states, data, data.shape[0], STRIDE, STREAM_LEN)
+    want = w["recs"].astype(MATCH_DTYPE)
+    want["stream"] = mine[w["recs"]["stream"]].astype(np.uint32)
+    records_ok = got.tolist() == want.tolist()
+    gather_ok = None
+    if dist is not None:
+        all_got = shard.gather_records(got, dist, device=dev)
+        all_want = shard.gather_records(want, dist, device=dev)
+        gather_ok = all_got.tolist() == all_want.tolist() and len({int(s) // n for s in all_want["stream"].tolist()} | {0}) >= 1
+        n_checked = int(all_want.size)
+    else:
+        n_checked = int(want.size)
+    flag = torch.tensor([1 if (records_ok and counts_vs_records and reduce_ok is not False and gather_ok is not False) else 0], device=dev)
+    if dist is not None:
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    out = {"checked_streams": int(sample.size), "shards_covered": int(len({int(s) // n for s in sample.tolist()})),
+           "records_checked": n_checked, "records_equal_oracle": records_ok, "counts_equal_record_histogram": counts_vs_records,
+           "allreduce_equals_sum_of_ranks": reduce_ok, "gathered_records_equal_oracle": gather_ok, "ok": bool(flag.item() == 1)}
+    if not out["ok"]:
+        raise SystemExit(f"bench.py: PARITY FAILURE (rank {rank}): {out}")
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -331,6 +412,19 @@ def ours_arm(args, rank, world, local_rank):
     if not args.no_e2e:
         e2e = run_e2e(args, torch, dist, nfa, batch, n, first, cap, n_states, n_matches, barrier, dev, world, sym_per_step)
 
+    parity = check_parity(torch, dist, shard, E, n_states, batch, n, first, world, rank, dev, counts, recs, int(r.n_records), n_dropped)
+
+    cap_ncu = ncu_capture().get(args.mix if args.ruleset == "snort_16" else "", {})
+    issue = None
+    if "warp_instructions_per_32_symbols" in cap_ncu:
+        sm_mhz = clocks.get("sm_mhz") or 1965.0
+        n_sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        peak_issue = n_sms * 4 * sm_mhz * 1e6                         # warp instructions per second, 4 schedulers per SM
+        used = cap_ncu["warp_instructions_per_32_symbols"] * (sym_per_step / 32.0) / (scan_ms * 1e-3)
+        issue = {"warp_instructions_per_32_symbols": cap_ncu["warp_instructions_per_32_symbols"],
+                 "active_threads_per_instruction": cap_ncu.get("threads_per_instruction"),
+                 "achieved": used / 1e9, "peak": peak_issue / 1e9, "unit": "G warp-instructions/s", "frac": used / peak_issue,
+                 "source": "profiles/r2_kernel.json (ncu --set full of this workload)"}
     if rank == 0:
         line = {
             "metric": metric_name(args), "value": value, "unit": "Gbit/s", "n_gpus": world, "steps": args.steps,
@@ -341,10 +435,15 @@ def ours_arm(args, rank, world, local_rank):
             "e2e": e2e,
             "gpu_launches": 2 * args.steps,
             "roofline": {"bound": "hbm", "kernel": "scan_lane_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": measured_traffic(sym_per_step),
-                         "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r1_traffic.json)", "peak_source": peak_src,
-                         "frac_of_8000": achieved / 8000.0, "scan_ms": scan_ms,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": (int(round(cap_ncu["dram_bytes_per_symbol"] * sym_per_step)) if "dram_bytes_per_symbol" in cap_ncu else None),
+                         "traffic_unit": "bytes per launch (ncu dram read+write of this workload at this size, profiles/r2_kernel.json)",
+                         "peak_source": peak_src, "frac_of_8000": achieved / 8000.0, "scan_ms": scan_ms,
                          "algorithmic_bytes_per_launch": sym_per_step},
+            # the limiter the HBM fraction does not show: warp instructions issued per 32 symbols (ncu, committed capture)
+            # against the SMs' issue rate at the clock sampled during this run
+            "roofline_issue": issue,
+            "parity": parity,
             "matches_per_step_rank0": n_matches, "rescanned_streams": n_rescanned, "records_dropped": n_dropped,
             "symbols_per_s": world * sym_per_step / (ms_per_step * 1e-3),
             "image": nfa.info,
@@ -360,12 +459,11 @@ def ours_arm(args, rank, world, local_rank):
             fb = O.b_scan_many(E, n_states, sample, 2 * n_pairs, STRIDE, STREAM_LEN, n_threads=threads, want_recs=False)
             dtb = time.perf_counter() - t0
             line["cpu_baseline"] = {
-                "value": s * 8 / dt / 1e9, "unit": "Gbit/s", "cores": threads, "kind": "port",
+                "value": s * 8 / dt / 1e9, "unit": "Gbit/s", "cores": threads, "kind": cpu_reference_kind(),
                 "sample": f"{n_pairs} (lo,hi) stream pairs x {STREAM_LEN} entries of the same {args.mix} workload "
                           f"({s} symbols, {dt:.1f} s wall)",
                 "simulated_cycles_per_s": c / dt,
-                "note": "oracle A = cycle-level C restatement of Design/FPGA.v + testbench; the Verilog itself cannot "
-                        "be simulated in this image",
+                "note": CPU_NOTE[cpu_reference_kind()],
                 "functional_port_gbit_s": 2 * n_pairs * STREAM_LEN * 8 / dtb / 1e9,
             }
         print(json.dumps(line), flush=True)

@@ -23,7 +23,7 @@ extern "C" {
 #endif
 
 /* 3: + rfb_nfa_describe, execution-image files, rfb_scan_submit / rfb_scan_wait (structs unchanged since 2)
- * 4: + rfb_nfa_calibrate / rfb_nfa_calibration (structs unchanged) */
+ * 4: + rfb_nfa_calibrate / rfb_nfa_calibration, rfb_group_* (structs unchanged) */
 #define RFB_ABI_VERSION 4
 
 typedef enum rfb_status {
@@ -221,6 +221,34 @@ int rfb_scan_collect(rfb_ctx *ctx, rfb_result *result);
 int rfb_scan_submit(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *batch, uint32_t flags,
                     rfb_result *result);
 int rfb_scan_wait(rfb_ctx *ctx, rfb_result **done);
+
+/* ---- multi-GPU groups (one process, N GPUs) -------------------------------------------------
+ * Replaces: nothing in the reference (one FPGA, one clock domain) -- this is how BASELINE config 4 is
+ * driven from a C host.  What makes it legal is the reference's own structure: its two streams share
+ * only reads of the transition memory (Design/FPGA.v:54-57,264-268) and every stream starts from the
+ * reset state {0} (FPGA.v:146-147), so streams shard freely.  A group is N contexts + N NCCL
+ * communicators (ncclCommInitAll; NCCL is loaded with dlopen at the first rfb_group_create, the
+ * library has no link-time dependency on it).  rfb_group_scan cuts a HOST batch into N contiguous
+ * stream shards, scans them concurrently (one host thread per GPU), SUM-all-reduces the per-state
+ * counts over NCCL and writes the shards' records, in shard order = canonical order when
+ * RFB_SCAN_SORT_RECORDS is set, into the caller's buffer.  Flags: RFB_SCAN_SORT_RECORDS,
+ * RFB_SCAN_FORCE_WARP, RFB_SCAN_NO_COUNTS.  gpu_ms is the maximum over the GPUs.
+ * A multi-process job (one process per GPU, as bench.py runs) uses rfb_ctx / rfb_scan per rank with
+ * stream_id_base and its own communicator instead; see INTEGRATION.md. */
+typedef struct rfb_group rfb_group;
+typedef struct rfb_group_nfa rfb_group_nfa;
+int rfb_group_create(const int *device_ids, int n, rfb_group **out);
+void rfb_group_destroy(rfb_group *group);
+int rfb_group_size(const rfb_group *group);
+rfb_ctx *rfb_group_ctx(rfb_group *group, int i);             /* member context (owned by the group) */
+const char *rfb_group_last_error(const rfb_group *group);
+int rfb_group_nfa_load_coe(rfb_group *group, const char *path, int64_t n_states, rfb_group_nfa **out);
+int rfb_group_nfa_from_entries(rfb_group *group, const uint32_t *entries, size_t n_entries,
+                               int64_t n_states, rfb_group_nfa **out);
+void rfb_group_nfa_destroy(rfb_group_nfa *nfa);
+rfb_nfa *rfb_group_nfa_member(rfb_group_nfa *nfa, int i);    /* member NFA on GPU i (owned by the handle) */
+int rfb_group_scan(rfb_group *group, const rfb_group_nfa *nfa, const rfb_batch *batch, uint32_t flags,
+                   rfb_result *result);
 
 /* Informational: the testbench's "Total no. cycles" (testbench_BLK_Mem.sv:52,84) for an M-entry
  * (lo,hi) trace pair, from the closed-form cycle model of Design/FPGA.v, evaluated on

@@ -63,6 +63,16 @@ SIGNATURES = {
     "rfb_scan_collect": (C.c_int, [_VP, C.POINTER(rfb_result)]),
     "rfb_scan_submit": (C.c_int, [_VP, _VP, C.POINTER(rfb_batch), C.c_uint32, C.POINTER(rfb_result)]),
     "rfb_scan_wait": (C.c_int, [_VP, C.POINTER(C.POINTER(rfb_result))]),
+    "rfb_group_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(_VP)]),
+    "rfb_group_destroy": (None, [_VP]),
+    "rfb_group_size": (C.c_int, [_VP]),
+    "rfb_group_ctx": (_VP, [_VP, C.c_int]),
+    "rfb_group_last_error": (C.c_char_p, [_VP]),
+    "rfb_group_nfa_load_coe": (C.c_int, [_VP, C.c_char_p, C.c_int64, C.POINTER(_VP)]),
+    "rfb_group_nfa_from_entries": (C.c_int, [_VP, _U32P, C.c_size_t, C.c_int64, C.POINTER(_VP)]),
+    "rfb_group_nfa_destroy": (None, [_VP]),
+    "rfb_group_nfa_member": (_VP, [_VP, C.c_int]),
+    "rfb_group_scan": (C.c_int, [_VP, _VP, C.POINTER(rfb_batch), C.c_uint32, C.POINTER(rfb_result)]),
     "rfb_fpga_cycles": (C.c_int, [_VP, _VP, _U8P, _U8P, C.c_uint32, C.POINTER(C.c_uint64)]),
 }
 

@@ -3,7 +3,9 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <string>
 #include <vector>
@@ -794,6 +796,9 @@ static int copy_chunks(rfb_ctx *ctx, const rfb_batch *b, uint8_t *d_data, unsign
     return RFB_OK;
 }
 
+// internal (rfb_group_scan): leave counts and records in the context's device buffers instead of copying them to the host
+static constexpr uint32_t SCAN_KEEP_ON_DEVICE = 0x80000000u;
+
 int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flags, rfb_result *res) {
     if (!ctx || !nfa || !res) return fail(ctx, RFB_E_INVALID, "NULL argument");
     if (nfa->ctx != ctx) return fail(ctx, RFB_E_INVALID, "nfa belongs to another context");
@@ -883,8 +888,10 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
         rc = sort_on_device(ctx, nfa, b, true, ctx->d_records, dr.n_records, st);
         if (rc) return rc;
     }
-    if (want_counts) CU(ctx, cudaMemcpyAsync(res->counts, ctx->d_counts, (size_t)nfa->host.n_states * 8, cudaMemcpyDeviceToHost, st));
-    if (dr.n_records) CU(ctx, cudaMemcpyAsync(res->records, ctx->d_records, dr.n_records * sizeof(rfb_match), cudaMemcpyDeviceToHost, st));
+    if (!(flags & SCAN_KEEP_ON_DEVICE)) {
+        if (want_counts) CU(ctx, cudaMemcpyAsync(res->counts, ctx->d_counts, (size_t)nfa->host.n_states * 8, cudaMemcpyDeviceToHost, st));
+        if (dr.n_records) CU(ctx, cudaMemcpyAsync(res->records, ctx->d_records, dr.n_records * sizeof(rfb_match), cudaMemcpyDeviceToHost, st));
+    }
     if (b->state_out && state_words) CU(ctx, cudaMemcpyAsync(b->state_out, ctx->d_state_out, state_words * 4, cudaMemcpyDeviceToHost, st));
     CU(ctx, cudaStreamSynchronize(st));
     res->n_matches = dr.n_matches; res->n_records = dr.n_records; res->n_dropped = dr.n_dropped;
@@ -1033,6 +1040,217 @@ int rfb_fpga_cycles(rfb_ctx *ctx, const rfb_nfa *nfa, const uint8_t *lo, const u
         rc = cuda_fail(ctx, e, "rfb_fpga_cycles");
     cudaFree(d_cost); cudaFree(d_tr); cudaFree(d_total);
     return rc;
+}
+
+// ---- multi-GPU in one process (BASELINE config 4) ------------------------------------------
+// A group is N contexts (one per GPU) plus one NCCL communicator per GPU (ncclCommInitAll).  rfb_group_scan cuts a
+// HOST batch into N contiguous stream shards (streams are independent: each starts from {0}, Design/FPGA.v:146-147,
+// and the two streams of the reference share only reads of the CSR, FPGA.v:54-57,264-268), scans every shard on its
+// GPU concurrently (one host thread per GPU, rfb_scan's chunked copy/scan overlap per GPU), then
+//   * per-state counts: ONE ncclAllReduce(sum, u64) over the device count vectors -- the path's only collective;
+//   * records: every shard's (already canonical) records are copied from its GPU straight to their place in the caller's
+//     buffer -- shards are ascending stream ranges, so the concatenation is the canonical order; the per-shard record
+//     counts are host values in a single process, so no collective is needed for them.
+// NCCL is loaded with dlopen when the first group is created: the library itself does not depend on it.
+}  // extern "C"
+
+namespace {
+typedef struct ncclComm *nccl_comm_t;
+struct NcclApi {
+    void *so = nullptr;
+    int (*CommInitAll)(nccl_comm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok() const { return CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd; }
+};
+constexpr int NCCL_UINT64 = 5, NCCL_SUM = 0;          // ncclUint64 / ncclSum (nccl.h; stable since NCCL 2.0)
+
+NcclApi &nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            a.so = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (a.so) break;
+        }
+        if (a.so) {
+            a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(dlsym(a.so, "ncclCommInitAll"));
+            a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(a.so, "ncclCommDestroy"));
+            a.AllReduce = reinterpret_cast<decltype(a.AllReduce)>(dlsym(a.so, "ncclAllReduce"));
+            a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(a.so, "ncclGroupStart"));
+            a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(a.so, "ncclGroupEnd"));
+            a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(a.so, "ncclGetErrorString"));
+        }
+        return a;
+    }();
+    return api;
+}
+}  // namespace
+
+struct rfb_group {
+    std::vector<rfb_ctx *> ctx;
+    std::vector<nccl_comm_t> comm;
+    std::string err;
+};
+struct rfb_group_nfa {
+    rfb_group *group = nullptr;
+    std::vector<rfb_nfa *> nfa;
+};
+
+static int group_fail(rfb_group *g, int code, const std::string &msg) {
+    g_err = msg;
+    if (g) g->err = msg;
+    return code;
+}
+
+extern "C" {
+
+int rfb_group_create(const int *device_ids, int n, rfb_group **out) {
+    if (!out || !device_ids || n < 1 || n > 64) return fail(nullptr, RFB_E_INVALID, "rfb_group_create: bad arguments");
+    *out = nullptr;
+    for (int i = 0; i < n; i++) for (int j = 0; j < i; j++)
+        if (device_ids[i] == device_ids[j]) return fail(nullptr, RFB_E_INVALID, "rfb_group_create: a device is listed twice");
+    NcclApi &api = nccl_api();
+    if (!api.ok()) return fail(nullptr, RFB_E_UNSUPPORTED, "NCCL (libnccl.so.2) could not be loaded: multi-GPU groups are unavailable");
+    rfb_group *g = new (std::nothrow) rfb_group();
+    if (!g) return fail(nullptr, RFB_E_NOMEM, "out of host memory");
+    for (int i = 0; i < n; i++) {
+        rfb_ctx *c = nullptr;
+        const int rc = rfb_ctx_create(device_ids[i], &c);
+        if (rc) { rfb_group_destroy(g); return rc; }
+        g->ctx.push_back(c);
+    }
+    g->comm.assign((size_t)n, nullptr);
+    const int nrc = api.CommInitAll(g->comm.data(), n, device_ids);
+    if (nrc != 0) {
+        const std::string msg = std::string("ncclCommInitAll: ") + (api.GetErrorString ? api.GetErrorString(nrc) : "failed");
+        g->comm.clear();
+        rfb_group_destroy(g);
+        return fail(nullptr, RFB_E_CUDA, msg);
+    }
+    *out = g;
+    return RFB_OK;
+}
+
+void rfb_group_destroy(rfb_group *g) {
+    if (!g) return;
+    for (nccl_comm_t c : g->comm) if (c) nccl_api().CommDestroy(c);
+    for (rfb_ctx *c : g->ctx) rfb_ctx_destroy(c);
+    delete g;
+}
+
+int rfb_group_size(const rfb_group *g) { return g ? (int)g->ctx.size() : 0; }
+rfb_ctx *rfb_group_ctx(rfb_group *g, int i) { return (g && i >= 0 && i < (int)g->ctx.size()) ? g->ctx[(size_t)i] : nullptr; }
+const char *rfb_group_last_error(const rfb_group *g) { return g ? g->err.c_str() : g_err.c_str(); }
+
+int rfb_group_nfa_from_entries(rfb_group *g, const uint32_t *entries, size_t n_entries, int64_t n_states, rfb_group_nfa **out) {
+    if (!g || !entries || !out) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    *out = nullptr;
+    rfb_group_nfa *gn = new (std::nothrow) rfb_group_nfa();
+    if (!gn) return group_fail(g, RFB_E_NOMEM, "out of host memory");
+    gn->group = g;
+    for (rfb_ctx *c : g->ctx) {                        // the plan is built once and cached (plan_build_cached); every GPU gets a copy
+        rfb_nfa *nfa = nullptr;
+        const int rc = rfb_nfa_from_entries(c, entries, n_entries, n_states, &nfa);
+        if (rc) { g->err = c->err; rfb_group_nfa_destroy(gn); return rc; }
+        gn->nfa.push_back(nfa);
+    }
+    *out = gn;
+    return RFB_OK;
+}
+
+int rfb_group_nfa_load_coe(rfb_group *g, const char *path, int64_t n_states, rfb_group_nfa **out) {
+    if (!g || !path || !out) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    std::vector<uint32_t> e;
+    std::string err;
+    const int rc = coe_parse_file(path, e, err);
+    if (rc) return group_fail(g, rc, err);
+    return rfb_group_nfa_from_entries(g, e.data(), e.size(), n_states, out);
+}
+
+void rfb_group_nfa_destroy(rfb_group_nfa *gn) {
+    if (!gn) return;
+    for (rfb_nfa *n : gn->nfa) rfb_nfa_destroy(n);
+    delete gn;
+}
+
+rfb_nfa *rfb_group_nfa_member(rfb_group_nfa *gn, int i) { return (gn && i >= 0 && i < (int)gn->nfa.size()) ? gn->nfa[(size_t)i] : nullptr; }
+
+int rfb_group_scan(rfb_group *g, const rfb_group_nfa *gn, const rfb_batch *b, uint32_t flags, rfb_result *res) {
+    if (!g || !gn || !b || !res) return fail(nullptr, RFB_E_INVALID, "NULL argument");
+    if (gn->group != g) return group_fail(g, RFB_E_INVALID, "nfa belongs to another group");
+    if (b->offsets || b->steps || b->state_in || b->state_out)
+        return group_fail(g, RFB_E_UNSUPPORTED, "rfb_group_scan takes uniformly strided batches without per-stream lengths or resumed state");
+    if (flags & ~(RFB_SCAN_SORT_RECORDS | RFB_SCAN_FORCE_WARP | RFB_SCAN_NO_COUNTS))
+        return group_fail(g, RFB_E_INVALID, "rfb_group_scan: unsupported flag");
+    int rc = check_batch(g->ctx[0], b, true);
+    if (rc) { g->err = g->ctx[0]->err; return rc; }
+    const size_t N = g->ctx.size();
+    const uint32_t n_states = gn->nfa[0]->host.n_states;
+    const bool want_counts = res->counts && !(flags & RFB_SCAN_NO_COUNTS);
+    // contiguous, balanced shards: GPU i scans streams [n*i/N, n*(i+1)/N)
+    std::vector<rfb_batch> sb(N);
+    std::vector<rfb_result> sr(N);
+    std::vector<int> src(N, RFB_OK);
+    std::vector<std::vector<uint64_t>> scratch(N);
+    for (size_t i = 0; i < N; i++) {
+        const uint64_t first = b->n_streams * i / N, last = b->n_streams * (i + 1) / N;
+        sb[i] = *b;
+        sb[i].n_streams = last - first;
+        sb[i].data = b->data ? b->data + first * b->stride : nullptr;
+        sb[i].data_bytes = last > first ? std::min<uint64_t>(b->data_bytes - first * b->stride, (last - first - 1) * b->stride + std::max<uint64_t>(b->n_steps, std::min<uint64_t>(b->stride, b->data_bytes - (last - 1) * b->stride))) : 0;
+        sb[i].stream_id_base = b->stream_id_base + (uint32_t)first;
+        std::memset(&sr[i], 0, sizeof(rfb_result));
+        if (want_counts) { scratch[i].assign(n_states, 0); sr[i].counts = scratch[i].data(); }
+        sr[i].records = res->records;                  // only its capacity matters: SCAN_KEEP_ON_DEVICE leaves the records on the GPU
+        sr[i].record_capacity = res->records ? res->record_capacity : 0;
+    }
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < N; i++)
+        th.emplace_back([&, i] { src[i] = rfb_scan(g->ctx[i], gn->nfa[i], &sb[i], flags | SCAN_KEEP_ON_DEVICE, &sr[i]); });
+    for (auto &t : th) t.join();
+    for (size_t i = 0; i < N; i++) if (src[i]) { g->err = g->ctx[i]->err; g_err = g->err; return src[i]; }
+    // ---- the path's one collective: SUM all-reduce of the per-state counts over NCCL ----
+    if (want_counts) {
+        NcclApi &api = nccl_api();
+        int nrc = api.GroupStart();
+        for (size_t i = 0; i < N && nrc == 0; i++) {
+            cudaSetDevice(g->ctx[i]->device);
+            nrc = api.AllReduce(g->ctx[i]->d_counts, g->ctx[i]->d_counts, n_states, NCCL_UINT64, NCCL_SUM, g->comm[i], g->ctx[i]->stream);
+        }
+        const int erc = api.GroupEnd();
+        if (nrc == 0) nrc = erc;
+        if (nrc != 0) return group_fail(g, RFB_E_CUDA, std::string("ncclAllReduce: ") + (api.GetErrorString ? api.GetErrorString(nrc) : "failed"));
+        cudaSetDevice(g->ctx[0]->device);
+        cudaError_t e = cudaMemcpyAsync(res->counts, g->ctx[0]->d_counts, (size_t)n_states * 8, cudaMemcpyDeviceToHost, g->ctx[0]->stream);
+        if (e != cudaSuccess) return group_fail(g, RFB_E_CUDA, std::string("D2H of the reduced counts: ") + cudaGetErrorString(e));
+    }
+    // ---- records: shard by shard to their place in the caller's buffer ----
+    uint64_t n_matches = 0, n_symbols = 0, n_rescanned = 0, at = 0;
+    uint32_t launches = 0;
+    float ms = 0.f;
+    for (size_t i = 0; i < N; i++) {
+        n_matches += sr[i].n_matches; n_symbols += sr[i].n_symbols; n_rescanned += sr[i].n_rescanned;
+        launches += sr[i].n_launches; ms = std::max(ms, sr[i].gpu_ms);
+        const uint64_t room = res->records ? res->record_capacity - at : 0;
+        const uint64_t take = std::min<uint64_t>(sr[i].n_records, room);
+        if (take) {
+            cudaSetDevice(g->ctx[i]->device);
+            cudaError_t e = cudaMemcpyAsync(res->records + at, g->ctx[i]->d_records, take * sizeof(rfb_match), cudaMemcpyDeviceToHost, g->ctx[i]->stream);
+            if (e != cudaSuccess) return group_fail(g, RFB_E_CUDA, std::string("D2H of the records: ") + cudaGetErrorString(e));
+            at += take;
+        }
+    }
+    for (size_t i = 0; i < N; i++) {
+        cudaSetDevice(g->ctx[i]->device);
+        cudaError_t e = cudaStreamSynchronize(g->ctx[i]->stream);
+        if (e != cudaSuccess) return group_fail(g, RFB_E_CUDA, std::string("rfb_group_scan: ") + cudaGetErrorString(e));
+    }
+    res->n_matches = n_matches; res->n_records = at; res->n_dropped = n_matches - at;
+    res->n_symbols = n_symbols; res->n_rescanned = n_rescanned; res->gpu_ms = ms; res->n_launches = launches;
+    return RFB_OK;
 }
 
 }  // extern "C"

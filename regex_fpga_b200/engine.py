@@ -355,3 +355,64 @@ class Nfa:
     def collect(self, r):
         _check(self._L.rfb_scan_collect(self.ctx._h, C.byref(r)), self.ctx._h)
         return r
+
+
+class Group:
+    """N GPUs in one process (rfb_group_*): contiguous stream shards, one NCCL all-reduce of the per-state counts."""
+
+    def __init__(self, device_ids):
+        self._L = _lib.load()
+        ids = (C.c_int * len(device_ids))(*device_ids)
+        h = C.c_void_p()
+        _check(self._L.rfb_group_create(ids, len(device_ids), C.byref(h)))
+        self._h = h
+        self.size = int(self._L.rfb_group_size(h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rfb_group_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc:
+            raise RfbError(rc, (self._L.rfb_group_last_error(self._h) or b"").decode())
+
+    def nfa_from_entries(self, entries, n_states=-1):
+        entries = np.ascontiguousarray(entries, dtype=np.uint32)
+        h = C.c_void_p()
+        self._check(self._L.rfb_group_nfa_from_entries(self._h, entries.ctypes.data_as(C.POINTER(C.c_uint32)), entries.size, n_states, C.byref(h)))
+        return GroupNfa(self, h)
+
+
+class GroupNfa:
+    def __init__(self, group, handle):
+        self.group, self._L, self._h = group, group._L, handle
+        info = rfb_nfa_info()
+        _check(self._L.rfb_nfa_get_info(self._L.rfb_group_nfa_member(self._h, 0), C.byref(info)))
+        self.n_states = int(info.n_states)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.rfb_group_nfa_destroy(self._h)
+            self._h = None
+
+    def scan(self, data, n_streams, n_steps, stride, record_capacity=1 << 20, flags=SCAN_SORT_RECORDS, stream_id_base=0):
+        data = np.ascontiguousarray(data, dtype=np.uint8).reshape(-1)
+        b = rfb_batch()
+        b.data = data.ctypes.data if data.size else None
+        b.data_bytes = data.size
+        b.n_streams, b.stride, b.n_steps, b.stream_id_base = n_streams, stride, n_steps, stream_id_base
+        counts = np.zeros(self.n_states, dtype=np.uint64)
+        records = np.empty(record_capacity, dtype=MATCH_DTYPE)
+        r = rfb_result()
+        r.counts = counts.ctypes.data
+        r.records = records.ctypes.data if record_capacity else None
+        r.record_capacity = record_capacity
+        self.group._check(self._L.rfb_group_scan(self.group._h, self._h, C.byref(b), flags, C.byref(r)))
+        return ScanResult(counts, records[: r.n_records], r, None)

@@ -37,6 +37,21 @@ int main(int argc, char **argv) {
             if (mc[p]) printf(s ? "match_count_2[%d] = %u\n" : "match_count[%d] = %u\n", p, mc[p] & 0x3FF);
         free(mc);
     }
+    /* the same run through a one-process group of GPUs (here: one): shards + NCCL all-reduce of the counts */
+    {
+        const int dev = 0;
+        rfb_group *grp; rfb_group_nfa *gnfa;
+        if (rfb_group_create(&dev, 1, &grp)) { fprintf(stderr, "%s\n", rfb_last_error(NULL)); return 1; }
+        if (rfb_group_nfa_load_coe(grp, argv[1], -1, &gnfa)) { fprintf(stderr, "%s\n", rfb_group_last_error(grp)); return 1; }
+        rfb_result g; memset(&g, 0, sizeof g);
+        g.counts = calloc(info.n_states, 8);
+        g.record_capacity = 1 << 20; g.records = malloc(g.record_capacity * sizeof(rfb_match));
+        if (rfb_group_scan(grp, gnfa, &b, RFB_SCAN_SORT_RECORDS, &g)) { fprintf(stderr, "%s\n", rfb_group_last_error(grp)); return 1; }
+        if (g.n_records != r.n_records || memcmp(g.records, r.records, r.n_records * sizeof(rfb_match)) ||
+            memcmp(g.counts, r.counts, info.n_states * 8)) { fprintf(stderr, "group scan differs\n"); return 1; }
+        free(g.counts); free(g.records);
+        rfb_group_nfa_destroy(gnfa); rfb_group_destroy(grp);
+    }
     uint64_t cycles = 0;
     if (rfb_fpga_cycles(ctx, nfa, lo, hi, M, &cycles)) { fprintf(stderr, "%s\n", rfb_last_error(ctx)); return 1; }
     printf("Total no. cycles: %llu\n", (unsigned long long)cycles);   /* TB:84 */

@@ -657,3 +657,53 @@ def test_auto_calibration_on_the_first_large_batch(gpu_ctx, snort):
     assert nfa.calibration()[0] is True
     want = O.b_scan_many(snort.entries, snort.n_states, data, n, 320, 300)
     assert recs_tuple(got.records) == recs_tuple(want["recs"]) and np.array_equal(got.counts, want["counts"])
+
+
+def test_two_shards_through_two_contexts_equal_one_shot(snort):
+    """BASELINE config 4 on one GPU: the batch is cut into two contiguous shards, each scanned by its OWN context (its own
+    copy of the NFA) with stream_id_base; merged counts and records must equal the one-shot scan and the oracle
+    (streams are independent: Design/FPGA.v:54-57,264-268)."""
+    from regex_fpga_b200 import shard
+    n, L, stride = 3001, 500, 512
+    data = WL.make_batch_numpy("wmix", snort.lo, snort.hi, n, L, stride, seed=0x5EED0400)
+    want = O.b_scan_many(snort.entries, snort.n_states, data, n, stride, L)
+    with R.Context(0) as one:
+        whole = one.nfa_from_entries(snort.entries).scan(data, n, n_steps=L, stride=stride)
+    assert recs_tuple(whole.records) == recs_tuple(want["recs"]) and np.array_equal(whole.counts, want["counts"])
+    counts, recs = np.zeros(snort.n_states, np.uint64), []
+    ctxs = [R.Context(0), R.Context(0)]
+    try:
+        for r, ctx in enumerate(ctxs):
+            first, cnt = shard.shard_range(n, r, 2)
+            nfa = ctx.nfa_from_entries(snort.entries)
+            part = nfa.scan(data[first:first + cnt], cnt, n_steps=L, stride=stride, stream_id_base=first)
+            counts += part.counts
+            recs += recs_tuple(part.records)
+    finally:
+        for ctx in ctxs:
+            ctx.close()
+    assert np.array_equal(counts, want["counts"])
+    assert recs == recs_tuple(want["recs"])          # shards are ascending and contiguous: concatenation is canonical order
+
+
+def test_group_scan_in_one_process(snort):
+    """rfb_group_*: N GPUs in one process: contiguous shards, NCCL all-reduce of the counts, records in shard
+    order.  One GPU always (a 1-rank communicator still goes through ncclAllReduce); every visible GPU when there are more."""
+    import torch
+    n, L, stride = 10001, 400, 416
+    data = WL.make_batch_numpy("wmix", snort.lo, snort.hi, n, L, stride, seed=0x5EED0500)
+    want = O.b_scan_many(snort.entries, snort.n_states, data, n, stride, L)
+    sizes = [1] + ([torch.cuda.device_count()] if torch.cuda.device_count() > 1 else [])
+    for g in sizes:
+        with R.Group(list(range(g))) as grp:
+            assert grp.size == g
+            nfa = grp.nfa_from_entries(snort.entries)
+            for _ in range(2):                                           # the second call reuses every staging buffer
+                got = nfa.scan(data, n, L, stride, record_capacity=1 << 18, stream_id_base=7)
+                assert got.n_matches == want["n_recs"] and got.n_dropped == 0 and got.n_symbols == n * L
+                assert np.array_equal(got.counts, want["counts"])
+                w = want["recs"]
+                assert recs_tuple(got.records) == list(zip((w["stream"] + 7).tolist(), w["pos"].tolist(), w["state"].tolist()))
+            small = nfa.scan(data, n, L, stride, record_capacity=100)   # overflow is counted, never undefined
+            assert small.n_records == 100 and small.n_dropped == want["n_recs"] - 100 and np.array_equal(small.counts, want["counts"])
+            nfa.close()
