@@ -90,7 +90,10 @@ int lane_ring_cap(const ImageHeader &h) {
 // rows of the start-DFA table staged into shared memory, and the (16-byte multiple) bytes copied for them
 uint32_t lane_hot_rows(const ImageHeader &h, uint32_t *copy_bytes) {
     static const long max_rows = [] { const char *e = getenv("RFB_HOT_ROWS"); return e ? atol(e) : 1L << 30; }();
-    const size_t used = (size_t)h.blob_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16;
+    // 6 KB of every SM stay free: the record sort of the previous batch (sort.cu: 1 KB static + 1 KB reserved per CTA) must
+    // be able to run beside a lane-kernel CTA, or the pipelined host path (rfb_scan_submit / _wait) stalls behind the scan
+    constexpr size_t CORESIDENT_RESERVE = 6 * 1024;
+    const size_t used = (size_t)h.blob_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16 + CORESIDENT_RESERVE;
     const size_t avail = used < MAX_DYN_SMEM ? (MAX_DYN_SMEM - used) & ~(size_t)15 : 0;
     const size_t row = (size_t)std::max<uint32_t>(1u, h.dfa_ncls) * 2;
     size_t rows = std::min<size_t>(std::max<uint32_t>(1u, h.dfa_states), avail / row);
@@ -265,6 +268,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     bool have = false;
     bool evt = false;                                   // the quiet run stopped in front of an event: STEP takes that symbol
     bool done = false;                                  // no stream left for this lane
+    bool parked = false;                                // host path: the lane holds a stream whose input chunk has not landed yet
 #ifdef RFB_STATS
     unsigned long long st_iter = 0, st_qruns = 0, st_qsteps = 0, st_qzero = 0, st_steps = 0, st_items = 0, st_qfast = 0;
 #define RFB_STAT(x) x
@@ -277,6 +281,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
         // entered by converged lanes (a lane that leaves a block early waits for the others at the next meeting point
         // instead of running ahead through private copies of the code).
         if (__all_sync(0xffffffffu, done)) break;
+        if (batch.chunk_streams && __all_sync(0xffffffffu, done || parked)) __nanosleep(500);   // nothing to do but wait for the copy
         RFB_STAT(if (!done) st_iter++;)
 #define RFB_NEXT_CHUNK()                                                                        \
         do {                                                                                     \
@@ -351,19 +356,22 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             }
             if (!have) {   // ---- next stream ----
                 for (;;) {
-                    sid = atomicAdd(&out.g->next_stream, 1u);
-                    if (sid >= batch.n_streams) break;
-                    nsteps = batch.steps ? batch.steps[sid] : batch.n_steps;
-                    if (nsteps == 0) {
-                        if (batch.state_out && !batch.state_append)
-                            carry_state(batch.state_in ? batch.state_in + (size_t)sid * (1u + batch.state_cap) : nullptr,
-                                        batch.state_out + (size_t)sid * (1u + batch.state_cap), batch.state_cap);
-                        continue;
+                    if (!parked) {
+                        sid = atomicAdd(&out.g->next_stream, 1u);
+                        if (sid >= batch.n_streams) break;
+                        nsteps = batch.steps ? batch.steps[sid] : batch.n_steps;
+                        if (nsteps == 0) {
+                            if (batch.state_out && !batch.state_append)
+                                carry_state(batch.state_in ? batch.state_in + (size_t)sid * (1u + batch.state_cap) : nullptr,
+                                            batch.state_out + (size_t)sid * (1u + batch.state_cap), batch.state_cap);
+                            continue;
+                        }
+                        if (batch.steps && batch.count_symbols) atomicAdd(&out.g->n_symbols, (unsigned long long)nsteps);
                     }
-                    if (batch.steps && batch.count_symbols) atomicAdd(&out.g->n_symbols, (unsigned long long)nsteps);
-                    if (batch.chunk_streams) {   // host path: wait until the H2D copy of this stream's chunk has landed
-                        const unsigned int need = sid / batch.chunk_streams + 1u;
-                        while (ld_acquire(batch.ready) < need) __nanosleep(256);
+                    if (batch.chunk_streams) {   // host path: has the H2D copy of this stream's chunk landed?  If not the lane
+                                                 // parks its stream and asks again next iteration: its warp-mates go on
+                        parked = ld_acquire(batch.ready) < sid / batch.chunk_streams + 1u;
+                        if (parked) break;
                     }
                     P0 = 0; P1 = 0; rp = 0; re = 0; d = 0; k = 0;
                     if (batch.state_in) {   // resume: the stream's active set as left by an earlier call
@@ -388,7 +396,8 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                     } else { ring_st(lb, h.start_id); re = ROW; }
                     break;
                 }
-                if (sid >= batch.n_streams) done = true;   // this lane is done
+                if (parked) {}
+                else if (sid >= batch.n_streams) done = true;   // this lane is done
                 else {
                     // input: aligned 16-byte chunks; the first one is shifted down to the stream's first byte
                     const uint8_t *sp = stream_ptr(batch, sid);
@@ -404,7 +413,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             // a stream whose transient set stays non-empty takes its next symbols here as well (up to RFB_STEP_REPS per
             // iteration): busy streams then need fewer iterations, each of which also pays for a quiet block
 #pragma unroll 1
-            for (int rep = 0; !done && rep < RFB_STEP_REPS; rep++) {
+            for (int rep = 0; !done && !parked && rep < RFB_STEP_REPS; rep++) {
                 if (rep != 0) {
                     if (!(have && k != nsteps && rp != re)) break;
                     if (nv == 0u) RFB_NEXT_CHUNK();
