@@ -358,6 +358,7 @@ def ours_arm(args, rank, world, local_rank):
         batch = WL.make_adversarial_torch(E, n_states, hi, n, dev, STREAM_LEN, STRIDE, first_stream=first)
     else:
         batch = WL.make_batch_torch(args.mix, lo, hi, n, dev, STREAM_LEN, STRIDE, SEED, first)
+    torch.cuda.synchronize()   # the generator ran on torch's default stream; the scans below use their own
     counts = torch.zeros(n_states, dtype=torch.int64, device=dev)
     cap = args.record_capacity
     recs = torch.empty(cap * 3, dtype=torch.int32, device=dev)

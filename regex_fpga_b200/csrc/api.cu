@@ -90,6 +90,10 @@ struct rfb_nfa {
     std::vector<Part> parts;           // >= 1; several when the tables of the whole NFA do not fit one SM
     NfaDev full{};                     // raw CSR of the whole NFA on the device (cycle model)
     uint32_t *d_full = nullptr;
+    // parts of a cut NFA that can share ONE lane-kernel launch (all with tables, same mask width and ring capacity)
+    NfaDev *d_parts = nullptr;
+    uint32_t multi_words = 0; int multi_cap = 0; size_t multi_smem = 0;
+    bool multi_ok = false;
 };
 
 static int fail(rfb_ctx *ctx, int code, const std::string &msg) {
@@ -337,6 +341,28 @@ static int nfa_from_plan(rfb_ctx *ctx, Plan &plan, rfb_nfa **out) {
         nfa->full.row_ptr = nfa->d_full;
         nfa->full.trans = nfa->d_full + nfa->host.n_states + 1;
     }
+    if (nfa->parts.size() > 1 && nfa->parts.size() <= MAX_MULTI_PARTS && !std::getenv("RFB_NO_MULTI")) {
+        std::vector<NfaDev> devs;
+        bool same = true;
+        for (const Part &p : nfa->parts) {
+            if (!p.img.ok) { same = false; break; }
+            NfaDev d = p.dev;
+            d.hot_rows = lane_hot_rows(d.h, &d.hot_bytes);
+            if (devs.empty()) { nfa->multi_words = d.h.sticky_words; nfa->multi_cap = lane_ring_cap(d.h); nfa->multi_smem = 0; }
+            same = same && d.h.sticky_words == nfa->multi_words && lane_ring_cap(d.h) == nfa->multi_cap;
+            nfa->multi_smem = std::max(nfa->multi_smem, lane_smem_bytes(d.h));
+            devs.push_back(d);
+        }
+        if (same && nfa->multi_cap > 0) {
+            cudaError_t e;
+            if ((e = cudaMalloc(reinterpret_cast<void **>(&nfa->d_parts), devs.size() * sizeof(NfaDev))) != cudaSuccess ||
+                (e = cudaMemcpy(nfa->d_parts, devs.data(), devs.size() * sizeof(NfaDev), cudaMemcpyHostToDevice)) != cudaSuccess) {
+                rfb_nfa_destroy(nfa);
+                return cuda_fail(ctx, e, "upload part table");
+            }
+            nfa->multi_ok = true;
+        }
+    }
     *out = nfa;
     return RFB_OK;
 }
@@ -412,6 +438,7 @@ void rfb_nfa_destroy(rfb_nfa *nfa) {
     cudaSetDevice(nfa->device);
     for (Part &p : nfa->parts) p.release();
     cudaFree(nfa->d_full);
+    cudaFree(nfa->d_parts);
     delete nfa;
 }
 
@@ -708,6 +735,24 @@ static int enqueue_kernels(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b,
     // a row no kernel writes must read as "overflow", never as stale memory
     if (b->state_out && b->n_streams)
         CU(ctx, cudaMemsetAsync(b->state_out, 0xFF, (size_t)b->n_streams * (1 + (size_t)b->state_cap) * 4, st));
+    od.q_rescan_n = nullptr; od.q_next_item = nullptr;
+    // A cut NFA whose parts all have tables: ONE launch, CTAs bound to parts (scan.cu: scan_lane_multi_kernel), then one
+    // hand-over pass per part.  Not when the final sets are wanted: parts append to the same rows, one after the other.
+    if (b->n_streams && nfa->multi_ok && !(flags & RFB_SCAN_FORCE_WARP) && !b->state_out) {
+        bd.count_symbols = 1u; bd.state_append = 0u;
+        CU(ctx, launch_scan_lane_multi(nfa->d_parts, (uint32_t)nfa->parts.size(), nfa->multi_words, nfa->multi_cap, nfa->multi_smem,
+                                       bd, od, ctx->n_sms, st));
+        (*launches)++;
+        bd.chunk_streams = 0;
+        for (size_t pi = 0; pi < nfa->parts.size(); pi++) {
+            OutDev op = od;
+            op.rescan = rescan + pi * (size_t)b->n_streams;
+            op.q_rescan_n = &g->part_rescan[pi];
+            op.q_next_item = &g->part_item[pi];
+            CU(ctx, launch_scan_warp(nfa->parts[pi].dev, bd, op, true, ctx->n_sms, st)); (*launches)++;
+        }
+        return RFB_OK;
+    }
     if (b->n_streams) {
         bool first = true;
         for (const Part &p : nfa->parts) {   // one pass over the batch per part; reports of different parts are disjoint
@@ -740,10 +785,11 @@ int rfb_scan_device(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
     cudaSetDevice(ctx->device);
     (void)cudaGetLastError();   // a stale error of an unrelated earlier call must not be blamed on this launch
     cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->stream;
-    if (ctx->rescan_cap < b->n_streams) CU(ctx, ensure(ctx->rescan, ctx->rescan_cap, (size_t)b->n_streams));
+    { const size_t want = (size_t)b->n_streams * (nfa->multi_ok ? nfa->parts.size() : 1); if (ctx->rescan_cap < want) CU(ctx, ensure(ctx->rescan, ctx->rescan_cap, want)); }
 
     if (flags & RFB_SCAN_ACCUMULATE) {
         CU(ctx, cudaMemsetAsync(&ctx->g->next_stream, 0, 3 * sizeof(unsigned int), st));
+        CU(ctx, cudaMemsetAsync(ctx->g->part_next, 0, 3 * MAX_MULTI_PARTS * sizeof(unsigned int), st));
     } else {
         CU(ctx, cudaMemsetAsync(ctx->g, 0, sizeof(ScanGlobals), st));
         if (res->counts && !(flags & RFB_SCAN_NO_COUNTS))
@@ -818,7 +864,7 @@ int rfb_scan(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32_t flag
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
     const size_t padded = ((size_t)b->data_bytes + 15) / 16 * 16 + 16;
     CU(ctx, ensure(ctx->d_data, ctx->d_data_cap, padded));
-    if (ctx->rescan_cap < b->n_streams) CU(ctx, ensure(ctx->rescan, ctx->rescan_cap, (size_t)b->n_streams));
+    { const size_t want = (size_t)b->n_streams * (nfa->multi_ok ? nfa->parts.size() : 1); if (ctx->rescan_cap < want) CU(ctx, ensure(ctx->rescan, ctx->rescan_cap, want)); }
     rfb_batch db = *b;
     db.data = ctx->d_data;
     if (b->offsets) {
@@ -933,7 +979,7 @@ int rfb_scan_submit(rfb_ctx *ctx, const rfb_nfa *nfa, const rfb_batch *b, uint32
     cudaStream_t st = ctx->stream, cs = ctx->copy_stream;
     const size_t padded = ((size_t)b->data_bytes + 15) / 16 * 16 + 16;
     CU(ctx, ensure(s.d_data, s.d_data_cap, padded));
-    if (s.rescan_cap < b->n_streams) CU(ctx, ensure(s.rescan, s.rescan_cap, (size_t)b->n_streams));
+    { const size_t want = (size_t)b->n_streams * (nfa->multi_ok ? nfa->parts.size() : 1); if (s.rescan_cap < want) CU(ctx, ensure(s.rescan, s.rescan_cap, want)); }
     rfb_batch db = *b;
     db.data = s.d_data;
     rfb_result dr = *res;

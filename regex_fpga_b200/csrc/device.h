@@ -16,7 +16,12 @@ struct ScanGlobals {
     unsigned int n_rescan_total;    // handed-over streams (accumulates when the three above are reset between launches)
     unsigned int chunks_ready;      // rfb_scan: input chunks whose H2D copy has completed (written by the copy stream)
     unsigned int pad[3];
+    // parts of a cut NFA scanned in one launch (scan_lane_multi_kernel): per-part stream fetch, hand-over count, hand-over fetch
+    unsigned int part_next[16];
+    unsigned int part_rescan[16];
+    unsigned int part_item[16];
 };
+constexpr uint32_t MAX_MULTI_PARTS = 16;
 
 struct BatchDev {
     const uint8_t *data;
@@ -43,7 +48,9 @@ struct OutDev {
     rfb_match *records;          // nullable
     unsigned long long capacity;
     ScanGlobals *g;
-    uint2 *rescan;               // (stream, first pos to report) pairs, capacity n_streams
+    uint2 *rescan;               // (stream, first pos to report) pairs, capacity n_streams (x parts in a multi-part launch)
+    const unsigned int *q_rescan_n;  // general kernel: hand-over queue to drain instead of g->n_rescan / g->next_item (NULL: those)
+    unsigned int *q_next_item;
 };
 
 struct NfaDev {
@@ -85,6 +92,8 @@ size_t warp_smem_bytes(uint32_t n_states, int warps_per_cta);
 // Enqueue the lane kernel (one thread per stream, tables in shared memory).
 cudaError_t launch_scan_lane(const NfaDev &nfa, const BatchDev &batch, const OutDev &out, int n_sms,
                              cudaStream_t stream);
+cudaError_t launch_scan_lane_multi(const NfaDev *d_parts, uint32_t n_parts, uint32_t sticky_words, int cap, size_t smem,
+                                   const BatchDev &batch, const OutDev &out, int n_sms, cudaStream_t stream);
 // Enqueue the general kernel (one warp per stream, CSR in global memory / L2).
 //   from_rescan = false: all streams of the batch;  true: the (stream, first_pos) pairs queued by the
 //   lane kernel -- the count is read on the device, so no host round trip is needed in between.

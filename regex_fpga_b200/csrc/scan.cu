@@ -214,10 +214,11 @@ __device__ __forceinline__ void shr_bytes(uint4 &v, uint32_t nb) {
     v.x = __funnelshift_r(x, y, sh); v.y = __funnelshift_r(y, z, sh); v.z = __funnelshift_r(z, w, sh); v.w = w >> sh;
 }
 
+// The body of the lane kernel.  q_next / q_rescan_n / q_rescan: the stream-fetch counter and the hand-over queue this
+// CTA works on (the batch's own, or -- when several parts of a cut NFA run in one launch -- those of the CTA's part).
 template <int W, int RING_CAP>
-__global__ void __launch_bounds__(LANE_THREADS, 1)
-scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
-    extern __shared__ __align__(128) uint8_t smem[];
+__device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &batch, const OutDev &out, unsigned int *q_next,
+                                          unsigned int *q_rescan_n, uint2 *q_rescan, uint8_t *smem) {
     const ImageHeader &h = nfa.h;
     constexpr uint32_t ROW = LANE_THREADS * 2;          // bytes between consecutive ring entries of one lane
     constexpr uint32_t RING = RING_CAP * ROW;
@@ -357,7 +358,7 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
             if (!have) {   // ---- next stream ----
                 for (;;) {
                     if (!parked) {
-                        sid = atomicAdd(&out.g->next_stream, 1u);
+                        sid = atomicAdd(q_next, 1u);
                         if (sid >= batch.n_streams) break;
                         nsteps = batch.steps ? batch.steps[sid] : batch.n_steps;
                         if (nsteps == 0) {
@@ -387,8 +388,8 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                             else { ring_st(lb + re, id); re = (re + ROW) & RMASK; }
                         }
                         if (!fits) {   // more transient members than the ring holds: the general kernel takes the whole stream
-                            const unsigned int slot = atomicAdd(&out.g->n_rescan, 1u);
-                            out.rescan[slot] = make_uint2(sid, 0u);
+                            const unsigned int slot = atomicAdd(q_rescan_n, 1u);
+                            q_rescan[slot] = make_uint2(sid, 0u);
                             continue;
                         }
                     } else if (h.start_id < nsb) {                                        // Design/FPGA.v:146-147
@@ -535,8 +536,8 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
                              // re-runs the stream and reports from step k on (after the last step there is nothing left to
                              // report, but the caller may want S_{n_steps}: only that kernel has it)
                     if (k < nsteps || batch.state_out) {
-                        const unsigned int slot_ = atomicAdd(&out.g->n_rescan, 1u);
-                        out.rescan[slot_] = make_uint2(sid, k);
+                        const unsigned int slot_ = atomicAdd(q_rescan_n, 1u);
+                        q_rescan[slot_] = make_uint2(sid, k);
                     }
                     have = false;
                 }
@@ -554,6 +555,35 @@ scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
 #undef RFB_NEXT_CHUNK
 }
 
+template <int W, int RING_CAP>
+__global__ void __launch_bounds__(LANE_THREADS, 1)
+scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    lane_body<W, RING_CAP>(nfa, batch, out, &out.g->next_stream, &out.g->n_rescan, out.rescan, smem);
+}
+
+// Several parts of a cut NFA (csrc/parts.cpp) in ONE launch: CTA b scans the whole batch against part b % n_parts, whose
+// tables it stages into its shared memory; every part has its own stream counter and hand-over queue.  The FPGA holds
+// the whole NFA in one memory and scans it in one pass (Design/FPGA.v:773-795); here the batch is still read once per
+// part, but by CTAs that run side by side: one kernel, one tail, streams spread over 148 / n_parts SMs per part instead
+// of a pass per part in which every lane gets one or two streams.
+template <int W, int RING_CAP>
+__global__ void __launch_bounds__(LANE_THREADS, 1)
+scan_lane_multi_kernel(const NfaDev *__restrict__ parts, const uint32_t n_parts, const BatchDev batch_in, const OutDev out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ NfaDev s_nfa;
+    const uint32_t p = blockIdx.x % n_parts;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(parts + p);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_nfa);
+        for (uint32_t i = threadIdx.x; i < sizeof(NfaDev) / 4; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    BatchDev batch = batch_in;
+    batch.count_symbols = batch_in.count_symbols && p == 0;       // ragged batches: the stream lengths are summed once
+    lane_body<W, RING_CAP>(s_nfa, batch, out, &out.g->part_next[p], &out.g->part_rescan[p], out.rescan + (size_t)p * batch.n_streams, smem);
+}
+
 cudaError_t launch_scan_lane(const NfaDev &nfa_in, const BatchDev &batch, const OutDev &out, int n_sms, cudaStream_t stream) {
     const size_t smem = lane_smem_bytes(nfa_in.h);
     NfaDev nfa = nfa_in;
@@ -564,6 +594,26 @@ cudaError_t launch_scan_lane(const NfaDev &nfa_in, const BatchDev &batch, const 
 
     const bool w1 = nfa.h.sticky_words == 1;
 #define RFB_LAUNCH(W_, C_) scan_lane_kernel<W_, C_><<<grid, LANE_THREADS, smem, stream>>>(nfa, batch, out)
+    if (cap == 64) { if (w1) RFB_LAUNCH(1, 64); else RFB_LAUNCH(2, 64); }
+    else if (cap == 32) { if (w1) RFB_LAUNCH(1, 32); else RFB_LAUNCH(2, 32); }
+    else if (cap == 16) { if (w1) RFB_LAUNCH(1, 16); else RFB_LAUNCH(2, 16); }
+    else return cudaErrorInvalidValue;
+#undef RFB_LAUNCH
+    return cudaGetLastError();
+}
+
+// parts[0..n_parts) on the device (hot_rows / hot_bytes already set), all with `sticky_words` and ring capacity `cap`
+cudaError_t launch_scan_lane_multi(const NfaDev *d_parts, uint32_t n_parts, uint32_t sticky_words, int cap, size_t smem,
+                                   const BatchDev &batch, const OutDev &out, int n_sms, cudaStream_t stream) {
+    if (n_parts == 0 || n_parts > MAX_MULTI_PARTS) return cudaErrorInvalidValue;
+    // every part gets the same number of CTAs (a CTA cannot help another part: the tables in its shared memory are its part's)
+    unsigned long long per_part = (batch.n_streams + LANE_THREADS - 1) / LANE_THREADS;
+    const unsigned long long max_per_part = std::max<unsigned long long>(1, (unsigned long long)n_sms / n_parts);
+    if (per_part > max_per_part) per_part = max_per_part;
+    if (per_part == 0) per_part = 1;
+    const int grid = (int)(per_part * n_parts);
+    const bool w1 = sticky_words == 1;
+#define RFB_LAUNCH(W_, C_) scan_lane_multi_kernel<W_, C_><<<grid, LANE_THREADS, smem, stream>>>(d_parts, n_parts, batch, out)
     if (cap == 64) { if (w1) RFB_LAUNCH(1, 64); else RFB_LAUNCH(2, 64); }
     else if (cap == 32) { if (w1) RFB_LAUNCH(1, 32); else RFB_LAUNCH(2, 32); }
     else if (cap == 16) { if (w1) RFB_LAUNCH(1, 16); else RFB_LAUNCH(2, 16); }
@@ -600,7 +650,10 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
 
     for (uint32_t w = lane; w < 2 * nw; w += 32) bits_cur[w] = 0;
     __syncwarp();
-    if (from_rescan && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&out.g->n_rescan_total, out.g->n_rescan);
+    // hand-over queue: the batch's own, or (parts of a cut NFA scanned in one launch) the part's
+    const unsigned int *q_n = out.q_rescan_n ? out.q_rescan_n : &out.g->n_rescan;
+    unsigned int *q_item = out.q_next_item ? out.q_next_item : &out.g->next_item;
+    if (from_rescan && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&out.g->n_rescan_total, *q_n);
 
     auto insert = [&](uint32_t t) {
         const uint32_t bit = 1u << (t & 31);
@@ -614,11 +667,11 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
     for (;;) {
         // ---- fetch a stream ----
         unsigned int item = 0;
-        if (lane == 0) item = atomicAdd(&out.g->next_item, 1u);
+        if (lane == 0) item = atomicAdd(q_item, 1u);
         item = __shfl_sync(0xffffffffu, item, 0);
         uint32_t sid, emit_from = 0;
         if (from_rescan) {
-            if (item >= out.g->n_rescan) break;
+            if (item >= *q_n) break;
             const uint2 r = out.rescan[item];
             sid = r.x; emit_from = r.y;
         } else {
@@ -793,6 +846,10 @@ cudaError_t launch_tb_cycles(const NfaDev &nfa, const uint32_t *cost, const uint
 cudaError_t configure_kernels() {
     cudaError_t e;
 #define RFB_ATTR(W_, C_) if ((e = cudaFuncSetAttribute(scan_lane_kernel<W_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM)) != cudaSuccess) return e
+    RFB_ATTR(1, 16); RFB_ATTR(2, 16); RFB_ATTR(1, 32); RFB_ATTR(2, 32); RFB_ATTR(1, 64); RFB_ATTR(2, 64);
+#undef RFB_ATTR
+    // (the multi-part kernel keeps its part's descriptor in 256 bytes of static shared memory)
+#define RFB_ATTR(W_, C_) if ((e = cudaFuncSetAttribute(scan_lane_multi_kernel<W_, C_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM - 1024)) != cudaSuccess) return e
     RFB_ATTR(1, 16); RFB_ATTR(2, 16); RFB_ATTR(1, 32); RFB_ATTR(2, 32); RFB_ATTR(1, 64); RFB_ATTR(2, 64);
 #undef RFB_ATTR
     if ((e = cudaFuncSetAttribute(tb_cycles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM)) != cudaSuccess) return e;

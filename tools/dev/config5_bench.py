@@ -19,7 +19,8 @@ for mix in ("adv", "whi"):
     else:
         batch = WL.make_batch_torch("whi", lo, hi, N, "cuda:0", seed=0x5EED0005)
     counts = torch.zeros(n7, dtype=torch.int64, device="cuda:0")
+    torch.cuda.synchronize()   # the generator ran on the default stream
     st = torch.cuda.Stream(); torch.cuda.set_stream(st)
-    for _ in range(2):
+    for _ in range(3):
         r = nfa.scan_device(batch.data_ptr(), batch.numel(), N, 1500, 1536, counts.data_ptr(), None, 0, cuda_stream=st.cuda_stream)
     print(mix, "streams", N, "gpu_ms", round(r.gpu_ms, 2), "Gbit/s", round(N * 1500 * 8 / r.gpu_ms / 1e6, 2), "matches", r.n_matches)

@@ -12,6 +12,7 @@ E, ns, lo, hi = z["entries"], int(z["n_states"]), z["lo"], z["hi"]
 ctx = R.Context(0); nfa = ctx.nfa_from_entries(E)
 batch = WL.make_adversarial_torch(E, ns, hi, n, "cuda:0", 1500, 1536) if mix == "adv" else WL.make_batch_torch(mix, lo, hi, n, "cuda:0", 1500, 1536)
 counts = torch.zeros(ns, dtype=torch.int64, device="cuda:0")
+torch.cuda.synchronize()
 for it in range(2):
     counts.zero_()
     r = nfa.scan_device(batch.data_ptr(), batch.numel(), n, 1500, 1536, counts.data_ptr(), None, 0, flags=R.SCAN_ACCUMULATE)
