@@ -483,7 +483,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mix", default="wmix", choices=["wmix", "whi", "wlo", "uniform", "adv"])
+    ap.add_argument("--mix", default="wmix", choices=["wmix", "whi", "wlo", "uniform", "adv", "wsplice"])
     ap.add_argument("--ruleset", default="snort_16", choices=["snort_16", "l7_filter"],
                     help="snort_16 is the headline (BASELINE.json); l7_filter is the reference's other shipped image")
     ap.add_argument("--streams", type=int, default=1 << 20, help="streams per GPU")

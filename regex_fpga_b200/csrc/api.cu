@@ -224,10 +224,17 @@ void rfb_ctx_destroy(rfb_ctx *ctx) {
 
 // ---- transition memory ---------------------------------------------------------------------------
 // builds the device copy of one part: edge-grouped CSR always, execution image when it fits
-static int upload_part(rfb_ctx *ctx, Part &p, uint32_t n_states_full, std::string &err) {
+static int upload_part(rfb_ctx *ctx, Part &p, uint32_t n_states_full, bool suppress_start_report, std::string &err) {
     cudaError_t e;
     int rc = ecsr_build(p.sub, p.ecsr, err);
     if (rc) return rc;
+    // the general kernel keeps two bit vectors and two lists per warp in shared memory: beyond ~400 K states it cannot run
+    if (warp_smem_bytes(p.sub.n_states, 1) > MAX_DYN_SMEM) {
+        err = "an NFA (part) of " + std::to_string(p.sub.n_states) + " states is beyond what the general kernel holds in shared memory";
+        return RFB_E_UNSUPPORTED;
+    }
+    p.dev.no_report_lane = 0xFFFFFFFFu; p.dev.no_report_sub = 0xFFFFFFFFu;
+    if (suppress_start_report) { p.dev.no_report_sub = 0; if (p.img.ok) p.dev.no_report_lane = p.img.id_of_orig[0]; }
     const Nfa &h = p.sub;
     const Ecsr &ec = p.ecsr;
 #define UP(ptr, vec, T)                                                                                             \
@@ -324,8 +331,11 @@ static int nfa_from_plan(rfb_ctx *ctx, Plan &plan, rfb_nfa **out) {
     }
     cudaSetDevice(ctx->device);
     std::string err;
-    for (Part &p : nfa->parts) {
-        const int rc = upload_part(ctx, p, nfa->host.n_states, err);
+    for (size_t g = 0; g < nfa->parts.size(); g++) {
+        Part &p = nfa->parts[g];
+        // state 0 as seen by this part (parts.cpp keeps only the part's share of its row): see NfaDev::no_report_*
+        const bool suppress = nfa->parts.size() > 1 && p.sub.degree(0) == 0 && (nfa->host.degree(0) != 0 || g > 0);
+        const int rc = upload_part(ctx, p, nfa->host.n_states, suppress, err);
         if (rc) { rfb_nfa_destroy(nfa); return rc == RFB_E_CUDA ? rc : fail(ctx, rc, err); }
     }
     if (nfa->parts.size() == 1) nfa->full = nfa->parts[0].dev;

@@ -74,6 +74,10 @@ struct NfaDev {
     const uint16_t *dfa_act;     // insertion lists: internal id | 0x8000 if another entry follows
     const uint32_t *dfa_mem_ptr; // [dfa_states + 1]: never-materialised members of each DFA state ...
     const uint16_t *dfa_mem_ids; // ... as internal ids
+    // A part of a cut NFA whose share of state 0's row is empty would see state 0 as a zero-out-degree (accepting) state
+    // although the full NFA's state 0 has edges (into other parts); a genuinely accepting state 0 is reported by the first
+    // part only.  no_report_lane / no_report_sub: the id (internal / sub-NFA) whose pulses this part must not report.
+    uint32_t no_report_lane, no_report_sub;
     uint32_t hot_rows, hot_bytes; // set per launch: rows of dfa_dt staged into shared memory / bytes copied for them (16-byte multiple)
     ImageHeader h;
 };

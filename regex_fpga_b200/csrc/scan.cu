@@ -289,6 +289,9 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
             cur = pre; nv = 16u;                                                                 \
             if (nsteps - k > 16u) { np += 16; pre = ld_in(np); }   /* the stream goes on behind it */ \
         } while (0)
+#pragma unroll 1
+      for (int qrep = 0; qrep < RFB_QUIET_REPS; qrep++) {
+        if (qrep != 0 && !__any_sync(0xffffffffu, have && !evt && rp == re && k < nsteps)) break;   // nobody left to run
         if (have && nv == 0u) RFB_NEXT_CHUNK();
         // ---- QUIET run: to the end of the bytes at hand, or to the first symbol with an event ----
         if (have && !evt && rp == re && nv != 0u && k < nsteps) {
@@ -347,6 +350,7 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
             if (nv && cnt) shr_bytes(cur, cnt);
         }
         __syncwarp();
+      }
         // ---- STEP: one whole symbol step ----
         if (!done && (!have || k == nsteps || (nv != 0u && (evt || rp != re)))) {
             if (have && k == nsteps) {                   // stream finished
@@ -485,7 +489,7 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
                             idx = u + (u >= gbase ? hc : 0u);
                             look = true;
                             if (u - acc_base < n_acc) {                   // accepting (Design/FPGA.v:210-226)
-                                emit_match_cold(out, sid + batch.stream_id_base, k + batch.pos_base, nfa.orig_of_id[u]);
+                                if (u != nfa.no_report_lane) emit_match_cold(out, sid + batch.stream_id_base, k + batch.pos_base, nfa.orig_of_id[u]);
                                 look = false;
                             }
                         } else if ((i0 | i1 | i2 | i3) != 0u) {          // row of a firing sticky state
@@ -707,7 +711,7 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
             // expand S_k through the edge-grouped rows: one active state per lane, its few edges serially
             auto expand = [&](uint32_t s) {
                 const uint32_t e0 = ep[s], e1 = ep[s + 1];
-                if (e0 == e1) { if (report) emit_match(out, sid + batch.stream_id_base, k + batch.pos_base, smap ? smap[s] : s); return; }   // FPGA.v:210-226
+                if (e0 == e1) { if (report && s != nfa.no_report_sub) emit_match(out, sid + batch.stream_id_base, k + batch.pos_base, smap ? smap[s] : s); return; }   // FPGA.v:210-226
                 for (uint32_t j = e0; j < e1; j++) {
                     const unsigned long long r = er[j];
                     const uint32_t lo = (uint32_t)r;
@@ -721,7 +725,7 @@ scan_warp_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out, const
                 for (uint32_t i = 0; i < ncur; i++) {
                     const uint32_t s = list_cur[i];
                     const uint32_t e0 = ep[s], e1 = ep[s + 1];
-                    if (e0 == e1 && report && lane == 0) emit_match(out, sid + batch.stream_id_base, k + batch.pos_base, smap ? smap[s] : s);   // FPGA.v:210-226
+                    if (e0 == e1 && report && lane == 0 && s != nfa.no_report_sub) emit_match(out, sid + batch.stream_id_base, k + batch.pos_base, smap ? smap[s] : s);   // FPGA.v:210-226
                     for (uint32_t j = e0 + lane; j < e1; j += 32) {
                         const unsigned long long r = er[j];
                         const uint32_t lo = (uint32_t)r;

@@ -41,9 +41,34 @@ def _source_select(mix, first_stream, n_streams):
     raise ValueError(mix)
 
 
+SPLICE_SEGMENTS = 8
+
+
+def splice_offsets(seed, first_stream, n_streams, n_windows):
+    """wsplice: (n_streams, SPLICE_SEGMENTS) window offsets, one per segment of every stream."""
+    j = np.arange(first_stream, first_stream + n_streams, dtype=np.uint64)[:, None]
+    q = np.arange(SPLICE_SEGMENTS, dtype=np.uint64)[None, :]
+    return (splitmix64_np(np.uint64(seed) ^ ((j << np.uint64(8)) | q) ^ np.uint64(0x5B11CE)) % np.uint64(n_windows)).astype(np.int64)
+
+
 def make_batch_numpy(mix, lo, hi, n_streams, stream_len=1500, stride=1536, seed=0x5EED0001, first_stream=0):
-    """Host batch as a (n_streams, stride) uint8 array."""
+    """Host batch as a (n_streams, stride) uint8 array.
+    wsplice: every stream is SPLICE_SEGMENTS windows (of the lo trace for even streams, the hi trace for odd ones) from
+    independent random offsets, back to back: the same byte statistics as W-mix but eight times the context switches, so
+    the start DFA visits far more distinct rows (a batch of plain windows re-reads the same 2 x 200 KB of text)."""
     out = np.zeros((n_streams, stride), dtype=np.uint8)
+    if mix == "wsplice":
+        lo = np.asarray(lo, dtype=np.uint8)
+        hi = np.asarray(hi, dtype=np.uint8)
+        seg = -(-stream_len // SPLICE_SEGMENTS)
+        n_windows = min(lo.size, hi.size) - seg + 1
+        offs = splice_offsets(seed, first_stream, n_streams, n_windows)
+        odd = (np.arange(first_stream, first_stream + n_streams) & 1).astype(bool)
+        wl = np.lib.stride_tricks.sliding_window_view(lo, seg)
+        wh = np.lib.stride_tricks.sliding_window_view(hi, seg)
+        rows = np.where(odd[:, None, None], wh[offs], wl[offs]).reshape(n_streams, SPLICE_SEGMENTS * seg)
+        out[:, :stream_len] = rows[:, :stream_len]
+        return out
     if mix == "uniform":
         n_words = (stream_len + 7) // 8
         ctr = (np.arange(first_stream, first_stream + n_streams, dtype=np.uint64)[:, None] << np.uint64(32)) | \
@@ -70,6 +95,19 @@ def make_batch_torch(mix, lo, hi, n_streams, device, stream_len=1500, stride=153
     """Device batch as a (n_streams, stride) uint8 torch tensor; byte-identical to make_batch_numpy."""
     import torch
     out = torch.zeros((n_streams, stride), dtype=torch.uint8, device=device)
+    if mix == "wsplice":
+        tl = torch.from_numpy(np.ascontiguousarray(lo, dtype=np.uint8)).to(device)
+        th = torch.from_numpy(np.ascontiguousarray(hi, dtype=np.uint8)).to(device)
+        seg = -(-stream_len // SPLICE_SEGMENTS)
+        n_windows = min(tl.numel(), th.numel()) - seg + 1
+        wl, wh = tl.unfold(0, seg, 1), th.unfold(0, seg, 1)
+        for s0 in range(0, n_streams, chunk):
+            n = min(chunk, n_streams - s0)
+            offs = torch.from_numpy(splice_offsets(seed, first_stream + s0, n, n_windows)).to(device)
+            odd = torch.from_numpy((np.arange(first_stream + s0, first_stream + s0 + n) & 1).astype(bool)).to(device)
+            rows = torch.where(odd[:, None, None], wh[offs], wl[offs]).reshape(n, SPLICE_SEGMENTS * seg)
+            out[s0:s0 + n, :stream_len] = rows[:, :stream_len]
+        return out
     if mix == "uniform":
         for s0 in range(0, n_streams, chunk):
             n = min(chunk, n_streams - s0)
