@@ -352,7 +352,8 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
         __syncwarp();
       }
         // ---- STEP: one whole symbol step ----
-        if (!done && (!have || k == nsteps || (nv != 0u && (evt || rp != re)))) {
+        const bool want_step = !done && (!have || k == nsteps || (nv != 0u && (evt || rp != re)));
+        if (want_step) {
             if (have && k == nsteps) {                   // stream finished
                 if (batch.state_out)
                     lane_export_state(nfa.orig_of_id, nfa.dfa_mem_ptr, nfa.dfa_mem_ids, batch.state_out + (size_t)sid * (1u + batch.state_cap),

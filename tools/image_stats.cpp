@@ -20,7 +20,7 @@ static uint64_t splitmix64(uint64_t x) {
     return z ^ (z >> 31);
 }
 
-struct Stats { double surv = 0, inj_useful = 0, t2hits = 0, entries = 0, lookups = 0, indirect = 0, cls = 0, pushes = 0, attn = 0, inj = 0, sticky = 0, symbols = 0, maxlist = 0; };
+struct Stats { double g_t2 = 0, g_attn = 0, g_ring2 = 0, g_nonsimple = 0, g_nextbad = 0, gen = 0, gen_simple = 0, surv = 0, inj_useful = 0, t2hits = 0, entries = 0, lookups = 0, indirect = 0, cls = 0, pushes = 0, attn = 0, inj = 0, sticky = 0, symbols = 0, maxlist = 0; };
 
 int main(int argc, char **argv) {
     if (argc < 4) return 1;
@@ -85,13 +85,14 @@ int main(int argc, char **argv) {
                     idx++;
                 }
             };
+            bool t2_flag = false, attn_real_flag = false;
             if (h.accel) {
                 d = std::max<uint32_t>(d, P[0] & 1);
                 const size_t at = (size_t)d * D.ncls + (cmap[c] & 0xFF);
                 d = D.dt[at] & 0x7FFF;
                 if (dhist.size() < D.n) dhist.resize(D.n, 0);
                 dhist[d]++;
-                if (D.dt[at] & 0x8000) { s.t2hits++; for (uint32_t q = D.dta[at];; q++) { push(D.act[q] & 0x7FFF); lk++; if (!(D.act[q] & 0x8000)) break; } }
+                if (D.dt[at] & 0x8000) { t2_flag = true; s.t2hits++; for (uint32_t q = D.dta[at];; q++) { push(D.act[q] & 0x7FFF); lk++; if (!(D.act[q] & 0x8000)) break; } }
             }
             s.entries += cur.size(); per_sym_entries[j][k] = cur.size();
             s.maxlist = std::max<double>(s.maxlist, cur.size());
@@ -106,7 +107,7 @@ int main(int argc, char **argv) {
                 for (uint32_t w = 0; w < W; w++) { im[w] = P[w] & M[w]; if (P[w] & ~K[w]) real = true; P[w] &= K[w]; }
                 if (k + 1 < L && !getenv("NO_LOOKAHEAD")) { const uint64_t *LK = (const uint64_t *)&img.blob[h.off_look + src[off + k + 1] * 8 * W]; for (uint32_t w = 0; w < W; w++) im[w] &= LK[w]; }
                 for (uint32_t w = 0; w < W; w++) if (im[w]) real = true;
-                if (real) s.attn++;
+                if (real) { s.attn++; attn_real_flag = true; }
             }
             for (uint32_t u : cur) {
                 if (u - h.acc_base < h.n_acc) { lk++; continue; }
@@ -115,6 +116,31 @@ int main(int argc, char **argv) {
             for (uint32_t w = 0; w < W; w++)
                 while (im[w]) { uint32_t b = __builtin_ctzll(im[w]) + 64 * w; im[w] &= im[w] - 1; s.inj++; any_surv = false; walk((sdesc[b] & 0xFFFF) + (hf & (sdesc[b] >> 16))); if (any_surv) s.inj_useful++; }
             s.lookups += lk; per_sym_lookups[j][k] = lk;
+            {   // classification of this symbol for the kernel's blocks
+                const uint32_t single_base = h.acc_base + h.n_acc;
+                auto simple = [&](uint32_t u) { return u >= single_base && u < h.gbase && (tab[u] & 0xFF) <= ((tab[u] >> 8) & 0xFF); };
+                const bool flagged = h.accel && false;
+                bool dfa_flag = false;
+                (void)flagged;
+                if (h.accel) { /* recompute: was the DFA transition of this symbol flagged? */ }
+                const bool ev_attn = attn_real_flag;
+                const bool ring_empty = cur.empty();
+                bool one_simple = cur.size() == 1 && simple(cur[0]);
+                bool next_ok = nxt.empty() || (nxt.size() == 1 && simple(nxt[0]));
+                const bool general = !ring_empty || ev_attn || t2_flag;
+                if (general) s.gen++;
+                if (general) {
+                    if (t2_flag) s.g_t2++;
+                    else if (ev_attn) s.g_attn++;
+                    else if (cur.size() >= 2) s.g_ring2++;
+                    else if (!one_simple) s.g_nonsimple++;
+                    else if (!next_ok) s.g_nextbad++;
+                }
+                // a symbol the extended quiet run could take: no flagged transition, no real attention, at most one simple transient
+                // state before and after
+                if (general && !ev_attn && !t2_flag && one_simple && next_ok) s.gen_simple++;
+                (void)dfa_flag;
+            }
             for (uint32_t w = 0; w < W; w++) P[w] |= Pn[w];
             cur.swap(nxt); nxt.clear(); s.symbols++;
         }
@@ -148,6 +174,8 @@ int main(int argc, char **argv) {
     for (int t = 0; t < 2; t++) {
         Stats &s = st[t];
         printf("%s: per symbol: pushes surviving the next symbol %.4f of %.4f; firings with a surviving target %.4f of %.4f\n", t ? "hi" : "lo", s.surv / s.symbols, s.pushes / s.symbols, s.inj_useful / s.symbols, s.inj / s.symbols);
+        printf("%s: general-step symbols per stream %.1f, of which a one-simple-transient-state quiet run could take %.1f\n", t ? "hi" : "lo", s.gen / s.symbols * L, s.gen_simple / s.symbols * L);
+        printf("%s:   first reason a general step is needed, per stream: flagged DFA transition %.1f, attention %.1f, >= 2 transient states %.1f, one non-simple state %.1f, successor not simple %.1f\n", t ? "hi" : "lo", s.g_t2 / s.symbols * L, s.g_attn / s.symbols * L, s.g_ring2 / s.symbols * L, s.g_nonsimple / s.symbols * L, s.g_nextbad / s.symbols * L);
         printf("%s: per symbol: t2hits %.3f entries %.3f lookups %.3f indirect %.3f class %.3f pushes %.3f attn %.3f inj %.3f sticky %.2f maxlist %.0f\n", t ? "hi" : "lo", s.t2hits / s.symbols,
                s.entries / s.symbols, s.lookups / s.symbols, s.indirect / s.symbols, s.cls / s.symbols, s.pushes / s.symbols, s.attn / s.symbols, s.inj / s.symbols, s.sticky / s.symbols, s.maxlist);
     }
