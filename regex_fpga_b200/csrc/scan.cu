@@ -195,9 +195,6 @@ __device__ __forceinline__ int ld_dfa(uint32_t d, uint32_t hot_rows, uint32_t ho
 __device__ __forceinline__ uint32_t lds16r(uint32_t a) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ int lds_s16(uint32_t a) { int v; asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
-#ifndef RFB_QUIET_REPS
-#define RFB_QUIET_REPS 1     // quiet runs per iteration of the flat loop
-#endif
 #ifndef RFB_QUIET_STEPS
 #define RFB_QUIET_STEPS 16   // symbols per quiet run (<= 16: one input chunk)
 #endif
@@ -289,9 +286,6 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
             cur = pre; nv = 16u;                                                                 \
             if (nsteps - k > 16u) { np += 16; pre = ld_in(np); }   /* the stream goes on behind it */ \
         } while (0)
-#pragma unroll 1
-      for (int qrep = 0; qrep < RFB_QUIET_REPS; qrep++) {
-        if (qrep != 0 && !__any_sync(0xffffffffu, have && !evt && rp == re && k < nsteps)) break;   // nobody left to run
         if (have && nv == 0u) RFB_NEXT_CHUNK();
         // ---- QUIET run: to the end of the bytes at hand, or to the first symbol with an event ----
         if (have && !evt && rp == re && nv != 0u && k < nsteps) {
@@ -350,7 +344,6 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
             if (nv && cnt) shr_bytes(cur, cnt);
         }
         __syncwarp();
-      }
         // ---- STEP: one whole symbol step ----
         const bool want_step = !done && (!have || k == nsteps || (nv != 0u && (evt || rp != re)));
         if (want_step) {
@@ -560,8 +553,10 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
 #undef RFB_NEXT_CHUNK
 }
 
+// 56 registers, not 58: 1024 threads x 64 (the allocation unit rounds 58 up) would take the whole register file and the
+// record sort of the previous batch could not run beside this kernel (pipelined host path: +1.9 ms per batch)
 template <int W, int RING_CAP>
-__global__ void __launch_bounds__(LANE_THREADS, 1)
+__global__ void __maxnreg__(56)
 scan_lane_kernel(const NfaDev nfa, const BatchDev batch, const OutDev out) {
     extern __shared__ __align__(128) uint8_t smem[];
     lane_body<W, RING_CAP>(nfa, batch, out, &out.g->next_stream, &out.g->n_rescan, out.rescan, smem);

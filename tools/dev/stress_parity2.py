@@ -46,7 +46,7 @@ with R.Context(0) as ctx:
         wrec = sorted(t for w in want for t in tup(w["recs"]))
         wcnt = sum(w["counts"] for w in want)
         for name, flags in (("lane", R.SCAN_SORT_RECORDS), ("warp", R.SCAN_SORT_RECORDS | R.SCAN_FORCE_WARP), ("lane-unsorted", 0)):
-            got = nfa.scan(data, ns, stride=0, offsets=offsets, steps=steps, record_capacity=1 << 20, flags=flags)
+            got = nfa.scan(data, ns, stride=0, offsets=offsets, steps=steps, record_capacity=1 << 22, flags=flags)
             g = tup(got.records)
             if (sorted(g) if flags == 0 else g) != wrec or not np.array_equal(got.counts, wcnt) or got.n_symbols != int(steps.sum()):
                 report(i, name, nfa)
