@@ -438,7 +438,7 @@ def ours_arm(args, rank, world, local_rank):
             "config": dict(workload_config(args, world), **({"cpus_bound_per_rank": numa} if numa else {})),
             "clocks": clocks,
             "e2e": e2e,
-            "gpu_launches": 2 * args.steps,
+            "gpu_launches": int(r.n_launches) * args.steps,   # per pass: lane kernel, second lane pass over the deferred streams, hand-over kernel
             "roofline": {"bound": "hbm", "kernel": "scan_lane_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (int(round(cap_ncu["dram_bytes_per_symbol"] * sym_per_step)) if "dram_bytes_per_symbol" in cap_ncu else None),
