@@ -84,7 +84,7 @@ __device__ __forceinline__ void stage_image(uint8_t *dst, const uint8_t *src, ui
 int lane_ring_cap(const ImageHeader &h) {
     static const int max_cap = [] { const char *e = getenv("RFB_RING_CAP"); const int v = e ? atoi(e) : 32; return v >= 64 ? 64 : v >= 32 ? 32 : 16; }();
     for (int cap = max_cap; cap >= 16; cap >>= 1)
-        if ((size_t)h.blob_bytes + (size_t)cap * LANE_THREADS * 2 + 16 <= MAX_DYN_SMEM) return cap;
+        if ((size_t)h.blob_bytes + (size_t)cap * LANE_THREADS * 2 + 16 + 256 <= MAX_DYN_SMEM) return cap;
     return 0;
 }
 // rows of the start-DFA table staged into shared memory, and the (16-byte multiple) bytes copied for them
@@ -93,7 +93,7 @@ uint32_t lane_hot_rows(const ImageHeader &h, uint32_t *copy_bytes) {
     // 6 KB of every SM stay free: the record sort of the previous batch (sort.cu: 1 KB static + 1 KB reserved per CTA) must
     // be able to run beside a lane-kernel CTA, or the pipelined host path (rfb_scan_submit / _wait) stalls behind the scan
     constexpr size_t CORESIDENT_RESERVE = 6 * 1024;
-    const size_t used = (size_t)h.blob_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16 + CORESIDENT_RESERVE;
+    const size_t used = (size_t)h.blob_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16 + 256 + CORESIDENT_RESERVE;
     const size_t avail = used < MAX_DYN_SMEM ? (MAX_DYN_SMEM - used) & ~(size_t)15 : 0;
     const size_t row = (size_t)std::max<uint32_t>(1u, h.dfa_ncls) * 2;
     size_t rows = std::min<size_t>(std::max<uint32_t>(1u, h.dfa_states), avail / row);
@@ -104,7 +104,7 @@ uint32_t lane_hot_rows(const ImageHeader &h, uint32_t *copy_bytes) {
 size_t lane_smem_bytes(const ImageHeader &h) {
     uint32_t hot_bytes = 0;
     lane_hot_rows(h, &hot_bytes);
-    return (size_t)h.blob_bytes + hot_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16;
+    return (size_t)h.blob_bytes + hot_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16 + 256;   // + barrier + byte-wide class table
 }
 
 // explicit shared-window accesses: 32-bit shared addresses never go through generic-pointer conversion.
@@ -192,6 +192,7 @@ __device__ __forceinline__ int ld_dfa(uint32_t d, uint32_t hot_rows, uint32_t ho
         : "+r"(v) : "r"(d), "r"(hot_rows), "r"(hot_s), "r"(at), "l"(base));
     return v;
 }
+__device__ __forceinline__ uint32_t lds8r(uint32_t a) { uint32_t v; asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds16r(uint32_t a) { uint32_t v; asm("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ int lds_s16(uint32_t a) { int v; asm("ld.shared.s16 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 
@@ -235,6 +236,15 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
     const uint32_t memb_s = sbase + h.off_memb, look_s = sbase + h.off_look;
     const uint32_t hot_s = sbase + h.blob_bytes, hot_rows = nfa.hot_rows;
     const uint32_t lb = __shfl_sync(0xffffffffu, sbase + h.blob_bytes + nfa.hot_bytes + threadIdx.x * 2, threadIdx.x & 31);   // ring entry at byte offset o: lb + o; bank-conflict free
+    // The quiet run looks the class of every symbol up: a byte-wide copy of that table (256 bytes = 64 words, so lanes that
+    // read the same word share one access and at most two words share a bank) instead of the 32-bit cmap entries (256
+    // words: ~3.5 conflicting accesses per warp-wide lookup -- on quiet traffic the shared-memory pipe was 91 % busy).
+    const uint32_t cls8_s = sbase + h.blob_bytes + nfa.hot_bytes + RING + 16;
+    if (threadIdx.x < 256) {
+        const uint32_t cm = lds32(cmap_s + threadIdx.x * 4);
+        asm volatile("st.shared.u8 [%0], %1;" ::"r"(cls8_s + threadIdx.x), "r"(cm & 0xFFu) : "memory");
+    }
+    __syncthreads();
     const uint32_t gbase = h.gbase, nsb = h.nsb;
     const uint32_t nbm = (1u << h.bucket_bits) - 1u;
     const uint32_t acc_base = h.acc_base, n_acc = h.n_acc, ncls = h.dfa_ncls;
@@ -301,7 +311,7 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
                 if (CHECK_N && (uint32_t)(J) >= n) break;                                                                  \
                 const uint32_t w = (J) < 4 ? cur.x : (J) < 8 ? cur.y : (J) < 12 ? cur.z : cur.w;                           \
                 const uint32_t cc = (w >> (8 * ((J) & 3))) & 0xFFu;                                                        \
-                const uint32_t cls = lds16r(cmap_s + cc * 4);      /* low half of cmap[cc] */                             \
+                const uint32_t cls = lds8r(cls8_s + cc);                                                                   \
                 uint32_t t = 0;                                                                                            \
                 if (needmask) {                                                                                            \
                     const uint32_t mrow = mask_s + cc * MSTRIDE;                                                           \
