@@ -145,7 +145,7 @@ static ImageOptions default_image_options() {
     if (const char *s = std::getenv("RFB_DFA_ABSORB")) opt.dfa_absorb = std::atoi(s);
     if (const char *s = std::getenv("RFB_DFA_STATES")) { const int v = std::atoi(s); if (v <= 0) opt.accel = 0; else opt.dfa_max_states = (uint32_t)v; }
     // the per-stream rings (16 entries x 1024 streams x 2 bytes) share the SM's shared memory with the tables
-    opt.max_bytes = (uint32_t)(MAX_DYN_SMEM - 16 * LANE_THREADS * 2 - 64 - 256);   // - barrier, byte-wide class table
+    opt.max_bytes = (uint32_t)(MAX_DYN_SMEM - 16 * LANE_THREADS * 2 - 64 - 256 - 4096);   // - barrier, the quiet run's class and attention tables
     return opt;
 }
 

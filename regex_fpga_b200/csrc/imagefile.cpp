@@ -69,7 +69,7 @@ int image_validate_structure(const Image &img, uint32_t n_states, std::string &e
     auto bad = [&](const char *what) { err = std::string("execution image is malformed: ") + what; return RFB_E_FORMAT; };
     const size_t B = img.blob.size();
     if (B != h.blob_bytes || B > (1u << 20)) return bad("blob size");
-    if (B + 16 * 1024 * 2 + 64 + 256 > 227 * 1024) return bad("tables do not fit one SM's shared memory beside the smallest rings");
+    if (B + 16 * 1024 * 2 + 64 + 256 + 4096 > 227 * 1024) return bad("tables do not fit one SM's shared memory beside the smallest rings");
     if (h.sticky_words != 1 && h.sticky_words != 2) return bad("sticky words");
     const uint32_t W = h.sticky_words;
     if (h.nsb != 64 * W || h.bucket_bits < 1 || h.bucket_bits > 6 || h.hash_shift > 7) return bad("header fields");

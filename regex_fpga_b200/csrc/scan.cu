@@ -81,10 +81,13 @@ __device__ __forceinline__ void stage_image(uint8_t *dst, const uint8_t *src, ui
 // kernel, which is an order of magnitude slower); what is left holds the first rows of the start-DFA table -- the
 // library keeps that table ordered by measured visit frequency (api.cu: calibration), and a row in shared memory
 // costs a bank-conflict-limited gather instead of one L1 wavefront per lane.
+// tables a CTA builds in shared memory at kernel start for the quiet run: byte-wide symbol classes (256 B) and the
+// attention masks at their natural stride (256 x 16 B reserved; 8 B used with a one-word mask)
+constexpr size_t LANE_AUX_BYTES = 256 + 256 * 16;
 int lane_ring_cap(const ImageHeader &h) {
     static const int max_cap = [] { const char *e = getenv("RFB_RING_CAP"); const int v = e ? atoi(e) : 32; return v >= 64 ? 64 : v >= 32 ? 32 : 16; }();
     for (int cap = max_cap; cap >= 16; cap >>= 1)
-        if ((size_t)h.blob_bytes + (size_t)cap * LANE_THREADS * 2 + 16 + 256 <= MAX_DYN_SMEM) return cap;
+        if ((size_t)h.blob_bytes + (size_t)cap * LANE_THREADS * 2 + 16 + LANE_AUX_BYTES <= MAX_DYN_SMEM) return cap;
     return 0;
 }
 // rows of the start-DFA table staged into shared memory, and the (16-byte multiple) bytes copied for them
@@ -93,7 +96,7 @@ uint32_t lane_hot_rows(const ImageHeader &h, uint32_t *copy_bytes) {
     // 6 KB of every SM stay free: the record sort of the previous batch (sort.cu: 1 KB static + 1 KB reserved per CTA) must
     // be able to run beside a lane-kernel CTA, or the pipelined host path (rfb_scan_submit / _wait) stalls behind the scan
     constexpr size_t CORESIDENT_RESERVE = 6 * 1024;
-    const size_t used = (size_t)h.blob_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16 + 256 + CORESIDENT_RESERVE;
+    const size_t used = (size_t)h.blob_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16 + LANE_AUX_BYTES + CORESIDENT_RESERVE;
     const size_t avail = used < MAX_DYN_SMEM ? (MAX_DYN_SMEM - used) & ~(size_t)15 : 0;
     const size_t row = (size_t)std::max<uint32_t>(1u, h.dfa_ncls) * 2;
     size_t rows = std::min<size_t>(std::max<uint32_t>(1u, h.dfa_states), avail / row);
@@ -104,7 +107,7 @@ uint32_t lane_hot_rows(const ImageHeader &h, uint32_t *copy_bytes) {
 size_t lane_smem_bytes(const ImageHeader &h) {
     uint32_t hot_bytes = 0;
     lane_hot_rows(h, &hot_bytes);
-    return (size_t)h.blob_bytes + hot_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16 + 256;   // + barrier + byte-wide class table
+    return (size_t)h.blob_bytes + hot_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16 + LANE_AUX_BYTES;   // + barrier + the tables built at kernel start
 }
 
 // explicit shared-window accesses: 32-bit shared addresses never go through generic-pointer conversion.
@@ -240,9 +243,21 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
     // read the same word share one access and at most two words share a bank) instead of the 32-bit cmap entries (256
     // words: ~3.5 conflicting accesses per warp-wide lookup -- on quiet traffic the shared-memory pipe was 91 % busy).
     const uint32_t cls8_s = sbase + h.blob_bytes + nfa.hot_bytes + RING + 16;
+    // ... and its attention masks are read for every symbol by every lane of a warp that holds any sticky state: in the
+    // image they sit in 32-byte (64-byte) rows together with K and M, i.e. on 4 (2) distinct bank groups, which makes a
+    // warp-wide lookup an ~8-way conflict (63 % of all shared-memory wavefronts on W-mix); a copy at stride 8 (16) bytes
+    // spreads them over all banks.
+    const uint32_t att_s = cls8_s + 256;
     if (threadIdx.x < 256) {
         const uint32_t cm = lds32(cmap_s + threadIdx.x * 4);
         asm volatile("st.shared.u8 [%0], %1;" ::"r"(cls8_s + threadIdx.x), "r"(cm & 0xFFu) : "memory");
+        if (W == 1) {
+            const uint2 a = lds64(mask_s + threadIdx.x * 32u * W);
+            asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(att_s + threadIdx.x * 8), "r"(a.x), "r"(a.y) : "memory");
+        } else {
+            const uint4 a = lds128(mask_s + threadIdx.x * 32u * W);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(att_s + threadIdx.x * 16), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w) : "memory");
+        }
     }
     __syncthreads();
     const uint32_t gbase = h.gbase, nsb = h.nsb;
@@ -315,8 +330,8 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
                 uint32_t t = 0;                                                                                            \
                 if (needmask) {                                                                                            \
                     const uint32_t mrow = mask_s + cc * MSTRIDE;                                                           \
-                    if (W == 1) { const uint2 a = lds64(mrow); t = (plo & a.x) | (phi & a.y); }                            \
-                    else { const uint4 a = lds128(mrow); t = (plo & a.x) | (phi & a.y) | (qlo & a.z) | (qhi & a.w); }      \
+                    if (W == 1) { const uint2 a = lds64(att_s + cc * 8); t = (plo & a.x) | (phi & a.y); }                  \
+                    else { const uint4 a = lds128(att_s + cc * 16); t = (plo & a.x) | (phi & a.y) | (qlo & a.z) | (qhi & a.w); } \
                     if (t != 0u && (uint32_t)((J) + 1) < n) {                                                              \
                         /* attention: a state that dies always counts; a state that fires only if what it enters can      \
                            outlive the NEXT symbol (look-ahead masks, image.cpp) -- most firings cannot */                 \
