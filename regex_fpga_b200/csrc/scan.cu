@@ -76,16 +76,18 @@ __device__ __forceinline__ void stage_image(uint8_t *dst, const uint8_t *src, ui
 // ------------------------------------------------------------------------------------------------
 // lane kernel
 // ------------------------------------------------------------------------------------------------
-// Shared memory of a lane-kernel CTA: image | hottest start-DFA rows | per-stream rings | barrier.
-// Ring entries per stream: 32 or 16, whatever fits beside the image (a full ring hands the stream to the general
-// kernel, which is an order of magnitude slower); what is left holds the first rows of the start-DFA table -- the
-// library keeps that table ordered by measured visit frequency (api.cu: calibration), and a row in shared memory
-// costs a bank-conflict-limited gather instead of one L1 wavefront per lane.
+// Shared memory of a lane-kernel CTA: image | hottest start-DFA rows | per-stream rings | barrier | class / attention copies.
+// The rows are the first ones of the start-DFA table -- the library keeps that table ordered by measured visit frequency
+// (api.cu: calibration), and a row in shared memory costs a bank-conflict-limited gather instead of one L1 wavefront per
+// lane.
 // tables a CTA builds in shared memory at kernel start for the quiet run: byte-wide symbol classes (256 B) and the
 // attention masks at their natural stride (256 x 16 B reserved; 8 B used with a one-word mask)
 constexpr size_t LANE_AUX_BYTES = 256 + 256 * 16;
 int lane_ring_cap(const ImageHeader &h) {
-    static const int max_cap = [] { const char *e = getenv("RFB_RING_CAP"); const int v = e ? atoi(e) : 32; return v >= 64 ? 64 : v >= 32 ? 32 : 16; }();
+    // 16 entries per stream: with the start DFA and the look-ahead masks no stream of the bench mixes (adversarial included)
+    // ever holds more transient states at once; a fuller stream goes to the general kernel, as with any capacity.  The 32 KB
+    // a 32-entry ring would add are worth more as L1 (below).
+    static const int max_cap = [] { const char *e = getenv("RFB_RING_CAP"); const int v = e ? atoi(e) : 16; return v >= 64 ? 64 : v >= 32 ? 32 : 16; }();
     for (int cap = max_cap; cap >= 16; cap >>= 1)
         if ((size_t)h.blob_bytes + (size_t)cap * LANE_THREADS * 2 + 16 + LANE_AUX_BYTES <= MAX_DYN_SMEM) return cap;
     return 0;
@@ -96,9 +98,15 @@ uint32_t lane_hot_rows(const ImageHeader &h, uint32_t *copy_bytes) {
     // 6 KB of every SM stay free: the record sort of the previous batch (sort.cu: 1 KB static + 1 KB reserved per CTA) must
     // be able to run beside a lane-kernel CTA, or the pipelined host path (rfb_scan_submit / _wait) stalls behind the scan
     constexpr size_t CORESIDENT_RESERVE = 6 * 1024;
-    const size_t used = (size_t)h.blob_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16 + LANE_AUX_BYTES + CORESIDENT_RESERVE;
-    const size_t avail = used < MAX_DYN_SMEM ? (MAX_DYN_SMEM - used) & ~(size_t)15 : 0;
+    // Shared memory and L1 share 256 KB per SM in fixed splits (... 164 / 196 / 228 KB of shared memory).  The rows that do not
+    // fit shared memory are served by L1 / L2, and a 60 KB L1 serves them far better than a 28 KB one (measured: W-mix
+    // 8.69 -> 8.23 ms with the same 333 rows): the kernel stays inside the 196 KB split when that still leaves room for a
+    // useful number of rows, and only takes the 228 KB split when the image is too large for that.
+    constexpr size_t SPLIT_196 = 196 * 1024 - 1024 - CORESIDENT_RESERVE;   // - the CTA's reserved KB
     const size_t row = (size_t)std::max<uint32_t>(1u, h.dfa_ncls) * 2;
+    const size_t used = (size_t)h.blob_bytes + (size_t)lane_ring_cap(h) * LANE_THREADS * 2 + 16 + LANE_AUX_BYTES;
+    const size_t limit = used + 64 * row <= SPLIT_196 ? SPLIT_196 : MAX_DYN_SMEM - CORESIDENT_RESERVE;
+    const size_t avail = used < limit ? (limit - used) & ~(size_t)15 : 0;
     size_t rows = std::min<size_t>(std::max<uint32_t>(1u, h.dfa_states), avail / row);
     if ((long)rows > max_rows) rows = (size_t)std::max<long>(0, max_rows);
     if (copy_bytes) *copy_bytes = (uint32_t)((rows * row + 15) & ~(size_t)15);
