@@ -633,15 +633,39 @@ static bool auto_calibrate_enabled() {
     return on;
 }
 
-// first large uniformly strided batch an NFA sees: measure on a strided sample of it (host or device memory)
+// Which streams of a batch are measured: one per block of `step` consecutive streams, at a hashed position inside the
+// block.  (A fixed stride aliases with any periodic structure of the batch: every 64th stream of a batch that alternates
+// two kinds of traffic is always the same kind -- the first version calibrated W-mix on its quiet half only.)
+__host__ __device__ static inline uint64_t calib_stream_index(uint64_t i, uint64_t step) {
+    uint64_t z = i + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return i * step + z % step;
+}
+__global__ void calib_gather_kernel(const uint8_t *__restrict__ data, uint64_t stride, uint64_t step, uint32_t n_steps, uint8_t *__restrict__ out) {
+    const uint8_t *src = data + calib_stream_index(blockIdx.x, step) * stride;
+    for (uint32_t i = threadIdx.x; i < n_steps; i += blockDim.x) out[(size_t)blockIdx.x * n_steps + i] = src[i];
+}
+
+// first large uniformly strided batch an NFA sees: measure on a sample of it (host or device memory)
 static int maybe_calibrate(rfb_ctx *ctx, const rfb_nfa *nfa_c, const rfb_batch *b, bool host) {
     rfb_nfa *nfa = const_cast<rfb_nfa *>(nfa_c);       // the device tables are a cache of the NFA, not part of its value
     if (nfa->calibrated || !auto_calibrate_enabled() || b->offsets || b->steps || b->n_streams < CALIB_MIN_STREAMS || b->n_steps < 64) return RFB_OK;
     const size_t n = CALIB_STREAMS, step = (size_t)(b->n_streams / n);
-    if (host) return calibrate_nfa(ctx, nfa, b->data, n, (size_t)b->stride * step, b->n_steps);
     std::vector<uint8_t> sample(n * (size_t)b->n_steps);
     cudaSetDevice(ctx->device);
-    CU(ctx, cudaMemcpy2D(sample.data(), b->n_steps, b->data, (size_t)b->stride * step, b->n_steps, n, cudaMemcpyDeviceToHost));
+    if (host) {
+        for (size_t i = 0; i < n; i++)
+            std::memcpy(&sample[i * b->n_steps], b->data + calib_stream_index(i, step) * b->stride, b->n_steps);
+    } else {
+        uint8_t *d_sample = nullptr;
+        CU(ctx, cudaMalloc(&d_sample, sample.size()));
+        calib_gather_kernel<<<(unsigned)n, 256>>>(b->data, b->stride, step, (uint32_t)b->n_steps, d_sample);
+        cudaError_t e = cudaMemcpy(sample.data(), d_sample, sample.size(), cudaMemcpyDeviceToHost);
+        cudaFree(d_sample);
+        CU(ctx, e);
+    }
     return calibrate_nfa(ctx, nfa, sample.data(), n, b->n_steps, b->n_steps);
 }
 

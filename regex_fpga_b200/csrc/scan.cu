@@ -329,22 +329,22 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
             const bool needmask = __ballot_sync(__activemask(), ((plo & ~abit) | phi | qlo | qhi) != 0u) != 0u;
             const uint32_t n = min(nv, nsteps - k);
             uint32_t cnt = 0;
-#define RFB_QUIET_STEP(J, CHECK_N)                                                                                         \
+            // one step of the run.  JJ: index of the symbol among the bytes at hand; W0 / W1: the registers that hold this
+            // symbol and the next one; JB: this symbol's (static) byte position in W0
+#define RFB_QUIET_STEP(JJ, JB, W0, W1, CHECK_N)                                                                            \
             {                                                                                                              \
-                if (CHECK_N && (uint32_t)(J) >= n) break;                                                                  \
-                const uint32_t w = (J) < 4 ? cur.x : (J) < 8 ? cur.y : (J) < 12 ? cur.z : cur.w;                           \
-                const uint32_t cc = (w >> (8 * ((J) & 3))) & 0xFFu;                                                        \
+                if (CHECK_N && (uint32_t)(JJ) >= n) break;                                                                 \
+                const uint32_t cc = __byte_perm((W0), 0u, 0x4440u | (uint32_t)(JB));   /* PRMT: one instruction */          \
                 const uint32_t cls = lds8r(cls8_s + cc);                                                                   \
                 uint32_t t = 0;                                                                                            \
                 if (needmask) {                                                                                            \
                     const uint32_t mrow = mask_s + cc * MSTRIDE;                                                           \
                     if (W == 1) { const uint2 a = lds64(att_s + cc * 8); t = (plo & a.x) | (phi & a.y); }                  \
                     else { const uint4 a = lds128(att_s + cc * 16); t = (plo & a.x) | (phi & a.y) | (qlo & a.z) | (qhi & a.w); } \
-                    if (t != 0u && (uint32_t)((J) + 1) < n) {                                                              \
+                    if (t != 0u && (uint32_t)(JJ) + 1u < n) {                                                              \
                         /* attention: a state that dies always counts; a state that fires only if what it enters can      \
                            outlive the NEXT symbol (look-ahead masks, image.cpp) -- most firings cannot */                 \
-                        const uint32_t wn = ((J) + 1) < 4 ? cur.x : ((J) + 1) < 8 ? cur.y : ((J) + 1) < 12 ? cur.z : cur.w; \
-                        const uint32_t cn = (wn >> (8 * (((J) + 1) & 3))) & 0xFFu;                                         \
+                        const uint32_t cn = __byte_perm((W1), 0u, 0x4440u | (((uint32_t)(JB) + 1u) & 3u));                 \
                         if (W == 1) {                                                                                      \
                             const uint4 km = lds128(mrow + 16);                                                            \
                             const uint2 lk = lds64(look_s + cn * 8);                                                       \
@@ -359,17 +359,20 @@ __device__ __forceinline__ void lane_body(const NfaDev &nfa, const BatchDev &bat
                 const int e = ld_dfa(d, hot_rows, hot_s, d * ncls + cls, dfa_dt);                                          \
                 if ((t | ((uint32_t)e & 0x80000000u)) != 0u) break;   /* STEP takes this symbol */                         \
                 d = (uint32_t)e;                                                                                           \
-                cnt = (uint32_t)((J) + 1);                                                                                 \
+                cnt = (uint32_t)(JJ) + 1u;                                                                                 \
             }
             // one version of the run for the whole warp: without per-step limit checks only if EVERY lane in the run has a
             // whole chunk ahead (two versions side by side would run one after the other)
-            if (__all_sync(__activemask(), n == (uint32_t)RFB_QUIET_STEPS)) {
+            const bool full = __all_sync(__activemask(), n == (uint32_t)RFB_QUIET_STEPS);
+#define RFB_WORD(J) ((J) < 4 ? cur.x : (J) < 8 ? cur.y : (J) < 12 ? cur.z : cur.w)
+            if (full) {
 #pragma unroll
-                for (int J = 0; J < RFB_QUIET_STEPS; J++) RFB_QUIET_STEP(J, false)
+                for (int J = 0; J < RFB_QUIET_STEPS; J++) RFB_QUIET_STEP(J, J & 3, RFB_WORD(J), RFB_WORD(J + 1), false)
             } else {
 #pragma unroll
-                for (int J = 0; J < RFB_QUIET_STEPS; J++) RFB_QUIET_STEP(J, true)
+                for (int J = 0; J < RFB_QUIET_STEPS; J++) RFB_QUIET_STEP(J, J & 3, RFB_WORD(J), RFB_WORD(J + 1), true)
             }
+#undef RFB_WORD
 #undef RFB_QUIET_STEP
             k += cnt; nv -= cnt;
             RFB_STAT(st_qruns++; st_qsteps += cnt; st_qzero += cnt == 0; st_qfast += n == 16u;)

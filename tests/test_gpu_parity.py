@@ -659,6 +659,29 @@ def test_auto_calibration_on_the_first_large_batch(gpu_ctx, snort):
     assert recs_tuple(got.records) == recs_tuple(want["recs"]) and np.array_equal(got.counts, want["counts"])
 
 
+def test_auto_calibration_sample_does_not_alias_with_the_batch(gpu_ctx, snort):
+    """W-mix alternates quiet (even) and busy (odd) streams.  A sample taken at a fixed even stride saw only the quiet
+    half (hot fraction 0.998, the busy half ran on cold rows); the hashed sample must see both kinds: its hot fraction lies
+    between the busy-only and the quiet-only one.  Host and device batches are sampled alike."""
+    import torch
+    n, L, stride = 16384, 1500, 1536
+    frac = {}
+    for mix in ("wlo", "whi", "wmix"):
+        nfa = gpu_ctx.nfa_from_entries(snort.entries)
+        data = WL.make_batch_numpy(mix, snort.lo, snort.hi, n, L, stride, seed=0x5EED0303)
+        nfa.scan(data, n, n_steps=L, stride=stride, record_capacity=0)
+        done, symbols, frac[mix] = nfa.calibration()
+        assert done and symbols == 2048 * (L - 1)
+    assert frac["whi"] + 0.02 < frac["wmix"] < frac["wlo"] - 0.02, frac
+    nfa = gpu_ctx.nfa_from_entries(snort.entries)
+    dev = torch.from_numpy(data).to("cuda:0")
+    counts = torch.zeros(snort.n_states, dtype=torch.int64, device="cuda:0")
+    torch.cuda.synchronize()
+    nfa.scan_device(dev.data_ptr(), dev.numel(), n, L, stride, counts.data_ptr(), None, 0, flags=0)
+    torch.cuda.synchronize()
+    assert nfa.calibration() == (True, 2048 * (L - 1), frac["wmix"])
+
+
 def test_two_shards_through_two_contexts_equal_one_shot(snort):
     """BASELINE config 4 on one GPU: the batch is cut into two contiguous shards, each scanned by its OWN context (its own
     copy of the NFA) with stream_id_base; merged counts and records must equal the one-shot scan and the oracle

@@ -23,3 +23,4 @@ names = ["lane-iterations", "quiet runs", "quiet steps", "quiet runs of 0 steps"
 print(mix, "streams", n, "gpu_ms", r.gpu_ms)
 for nm, v in zip(names, c):
     print(f"  {nm:32s} {v:14.0f}  per stream {v / n:9.1f}  per symbol {v / sym:.4f}")
+print("  calibration (measured, sample symbols, hot fraction):", nfa.calibration())
