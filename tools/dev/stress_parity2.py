@@ -42,7 +42,11 @@ with R.Context(0) as ctx:
         for s in range(ns):
             pos += int(gaps[s]); offsets[s] = pos; pos += int(steps[s])
         data = random_streams(rng, syms, 1, pos + 16, p_alpha=float(rng.choice([0.7, 0.95])))[0]
-        want = [O.b_scan(E, n, data[int(offsets[s]):int(offsets[s]) + int(steps[s])], int(steps[s]), stream_id=s, cap=1 << 18) for s in range(ns)]
+        want = [O.b_scan(E, n, data[int(offsets[s]):int(offsets[s]) + int(steps[s])], int(steps[s]), stream_id=s, cap=1 << 20) for s in range(ns)]
+        if any(w["n_recs"] > (1 << 20) for w in want) or sum(w["n_recs"] for w in want) > (1 << 22):
+            # the checker's own buffers would truncate (a replicated NFA multiplies every match by its copies): not a case
+            print("SKIP case", i, "more records than the checker keeps", flush=True)
+            continue
         wrec = sorted(t for w in want for t in tup(w["recs"]))
         wcnt = sum(w["counts"] for w in want)
         for name, flags in (("lane", R.SCAN_SORT_RECORDS), ("warp", R.SCAN_SORT_RECORDS | R.SCAN_FORCE_WARP), ("lane-unsorted", 0)):
