@@ -191,7 +191,8 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
 // start-DFA entry, sign-extended: negative <=> the transition has an insertion list
 __device__ __forceinline__ int ldg_s16(const uint16_t *p) { int v; asm("ld.global.nc.s16 %0, [%1];" : "=r"(v) : "l"(p)); return v; }
 // start-DFA entry `at` (= d * ncls + class) of state d: rows below hot_rows from shared memory, the rest from global
-// memory; predicated, no branch
+// memory; predicated, no branch.  Used by the general step; the quiet run reads the entry with one generic load from a
+// selected base instead (lane_body: RFB_LD_DFA_Q), which is two instructions shorter.
 __device__ __forceinline__ int ld_dfa(uint32_t d, uint32_t hot_rows, uint32_t hot_s, uint32_t at, const uint16_t *base) {
     int v = 0;   // defined on every path as far as ptxas can tell (the two loads are complementary)
     asm("{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t.reg .u32 sa;\n\t"
