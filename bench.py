@@ -255,7 +255,7 @@ PARITY_SAMPLE = 1024
 
 def check_parity(torch, dist, shard, E, n_states, batch, n, first, world, rank, dev, counts, recs, n_records, n_dropped):
     """What the last pass of THIS run computed, against the CPU oracle, at every N (outside the timed regions):
-      * records of a strided sample of PARITY_SAMPLE global stream ids spanning every shard: each rank copies its
+      * records of a sample of PARITY_SAMPLE global stream ids spanning every shard: each rank copies its
         sampled streams back from its device batch, scans them with oracle B, and compares with the records the GPU
         wrote for exactly those streams (global ids via stream_id_base); shard.gather_records then brings both sides
         to every rank and rank 0 compares the concatenations (the gather path);
@@ -265,7 +265,13 @@ def check_parity(torch, dist, shard, E, n_states, batch, n, first, world, rank, 
     from oracle import oracle_py as O
     from regex_fpga_b200.engine import MATCH_DTYPE
     total = n * world
-    sample = np.unique((np.arange(PARITY_SAMPLE, dtype=np.int64) * total) // PARITY_SAMPLE)
+    # one stream from each of PARITY_SAMPLE equal blocks of the global id range, at a hashed position inside the block (a
+    # fixed stride would alias with the batch: every 1024th stream of W-mix is a quiet one)
+    from regex_fpga_b200.workloads import splitmix64_np
+    blk = np.arange(PARITY_SAMPLE, dtype=np.int64)
+    lo_id, hi_id = (blk * total) // PARITY_SAMPLE, ((blk + 1) * total) // PARITY_SAMPLE
+    jitter = (splitmix64_np(blk.astype(np.uint64) ^ np.uint64(0x9A217E)) % np.maximum(hi_id - lo_id, 1).astype(np.uint64)).astype(np.int64)
+    sample = np.unique(np.minimum(lo_id + jitter, total - 1))
     mine = sample[(sample >= first) & (sample < first + n)]
     rec = recs[: 3 * n_records].view(-1, 3)
     hist = torch.zeros(n_states, dtype=torch.int64, device=dev)
